@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline measurement (BASELINE.json configs[1]):
+2^20-row synthetic trace, LDE (Circle iFFT + FFT, blow-up 2) + Blake2s Merkle commit of the reference's three
+trace trees (27 preprocessed + 347 main + 1012 interaction M31 columns) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+
+One "step" = one pass of the commit path over one 2^20-row trace segment per GPU (weak scaling: every rank
+commits its own segment, then the Merkle roots are all-gathered over NCCL).  `value` = rows committed per
+second by the whole job with inputs resident in HBM; `e2e` = the same through the C ABI from pinned HOST
+buffers (H2D of the evaluations and D2H of the roots inside the timed region).
+Inputs (5.4 GiB per segment) are larger than L2, so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P = (1 << 31) - 1
+METRIC = "RISC-V cycles proved/sec @ 2^20 rows"
+UNIT = "cycles/s"
+TREE_COLS = (27, 347, 1012)  # preprocessed+program, main, interaction (SURVEY.md §8 sizing shorthand)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-rows", type=int, default=20)
+    ap.add_argument("--cols", default=",".join(map(str, TREE_COLS)))
+    ap.add_argument("--log-blowup", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-cols", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_trace_torch(torch, dev, log_rows, tree_cols, seed):
+    """Synthetic fixed-length trace in the shape of the reference's three trees (uniform/byte-valued words)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0000 + seed)
+    n = 1 << log_rows
+    out = []
+    for t, c in enumerate(tree_cols):
+        hi = 256 if t == 1 else P  # main trace is mostly byte limbs / flags; the rest uniform in [0, P)
+        out.append(torch.randint(0, hi, (c, n), generator=g, device=dev, dtype=torch.int32))
+    return out
+
+
+def cpu_commit_sample(orc, np, log_rows, log_blowup, sample_cols, seed=1):
+    """The oracle's commit (iFFT + LDE + Merkle) over `sample_cols` columns; returns seconds."""
+    rng = np.random.default_rng(seed)
+    ev = rng.integers(0, P, (sample_cols, 1 << log_rows), dtype=np.uint32)
+    orc.twiddles(log_rows + log_blowup)  # twiddle precompute is not part of the timed path (done once per proof)
+    orc.twiddles(log_rows)
+    t0 = time.perf_counter()
+    _, lde = orc.interpolate_evaluate_batch(ev, log_blowup)
+    orc.merkle_commit(list(lde))
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (the real reference cannot be built here: Rust + un-vendored stwo, no cargo)."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tree_cols = [int(x) for x in args.cols.split(",")]
+    total_cols = sum(tree_cols)
+    sample = min(args.cpu_sample_cols, total_cols)
+    cores = orc.num_threads()
+    for _ in range(min(args.warmup, 1)):
+        cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, max(2, sample // 8))
+    ts = [cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample, seed=s) for s in range(max(1, min(args.steps, 3)))]
+    t = sum(ts) / len(ts)
+    t_full = t * total_cols / sample
+    value = (1 << args.log_rows) / t_full
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1),
+            "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (M31)",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, tree_cols),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle), scaled linearly in columns"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, tree_cols):
+    return {"workload": f"configs[1]: 2^{args.log_rows}-row synthetic trace, LDE (blow-up {1 << args.log_blowup}) + Blake2s Merkle commit of "
+                        f"{len(tree_cols)} trees ({'+'.join(map(str, tree_cols))} M31 columns) per GPU",
+            "log_rows": args.log_rows, "columns": sum(tree_cols), "log_blowup": args.log_blowup,
+            "l2": "inputs (5.4 GiB/segment) larger than L2; no flush needed", "sharding": "one trace segment per GPU + NCCL allgather of Merkle roots"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import nexus_zkvm_b200 as nb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    tree_cols = [int(x) for x in args.cols.split(",")]
+    total_cols = sum(tree_cols)
+    n_rows = 1 << args.log_rows
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = nb.Context(local, stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        evals_t = synth_trace_torch(torch, dev, args.log_rows, tree_cols, seed=rank)
+        evals = [ctx.wrap_device(t.data_ptr(), t.shape[0], args.log_rows) for t in evals_t]
+        ctx.precompute_twiddles(args.log_rows + args.log_blowup)
+        roots_dev = torch.zeros((len(tree_cols), 32), dtype=torch.uint8, device=dev)
+        gathered = [torch.zeros_like(roots_dev) for _ in range(world)] if world > 1 else None
+
+        state = {"coeffs": [None] * len(tree_cols), "ldes": [None] * len(tree_cols), "trees": [None] * len(tree_cols)}
+
+        def step():
+            roots = []
+            for t in range(len(tree_cols)):
+                if state["trees"][t] is not None:
+                    state["trees"][t].free()
+                co, ld, tree = ctx.commit_evals([evals[t]], args.log_blowup,
+                                                coeffs=[state["coeffs"][t]] if state["coeffs"][t] is not None else None,
+                                                ldes=[state["ldes"][t]] if state["ldes"][t] is not None else None)
+                state["coeffs"][t], state["ldes"][t], state["trees"][t] = co[0], ld[0], tree
+                roots.append(tree.root)
+            if world > 1:
+                roots_dev.copy_(torch.frombuffer(bytearray(b"".join(roots)), dtype=torch.uint8).view(len(tree_cols), 32), non_blocking=True)
+                dist.all_gather(gathered, roots_dev)
+            return roots
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            roots = step()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            roots = step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        launches = (ctx.launches - l0) * world
+        ms_per_step = ms_total / args.steps
+        value = world * n_rows / (ms_per_step * 1e-3)
+
+        # ---- per-stage breakdown + roofline (rank 0) : CUDA events on the launching stream
+        stages, roofline = None, None
+        if rank == 0 and not args.no_breakdown:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+            t_ifft = t_fft = t_mrk = 0.0
+            reps = 3
+            for t in range(len(tree_cols)):
+                scratch = torch.empty_like(evals_t[t])
+                sc = ctx.wrap_device(scratch.data_ptr(), tree_cols[t], args.log_rows)
+                for rep in range(reps + 1):
+                    scratch.copy_(evals_t[t])
+                    a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+                    a.record(stream); ctx.interpolate(sc); b.record(stream)
+                    lde = state["ldes"][t]
+                    lib_eval(ctx, sc, args.log_blowup, lde); c.record(stream)
+                    tr = ctx.merkle_commit([lde]); d.record(stream)
+                    torch.cuda.synchronize()
+                    tr.free()
+                    if rep > 0:
+                        t_ifft += a.elapsed_time(b) / reps; t_fft += b.elapsed_time(c) / reps; t_mrk += c.elapsed_time(d) / reps
+                del scratch
+            elems = total_cols * n_rows
+            fft_bytes = 12.0 * elems  # fused LDE commit = read 4 + write 8 per trace element
+            ach = fft_bytes / ((t_ifft + t_fft) * 1e-3) / 1e9
+            stages = {"ifft_ms": t_ifft, "lde_fft_ms": t_fft, "merkle_ms": t_mrk,
+                      "ifft_GBps_8B_per_elem": 8.0 * elems / (t_ifft * 1e-3) / 1e9,
+                      "lde_fft_GBps_12B_per_elem": 12.0 * elems / (t_fft * 1e-3) / 1e9,
+                      "merkle_GBps_read": (4.0 * elems * (1 << args.log_blowup)) / (t_mrk * 1e-3) / 1e9,
+                      "fft_Melems_per_s": (elems * (1 + (1 << args.log_blowup))) / ((t_ifft + t_fft) * 1e-3) / 1e6}
+            roofline = {"bound": "hbm", "kernel": "fft_pass_kernel (Circle iFFT + LDE FFT, all passes)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
+                        "time_share": {"fft": (t_ifft + t_fft) / (t_ifft + t_fft + t_mrk), "merkle": t_mrk / (t_ifft + t_fft + t_mrk)}}
+
+        # ---- e2e: host buffers -> C ABI -> roots on the host, copies inside the timed region
+        e2e = None
+        if not args.no_e2e:
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in evals_t]
+            for h, t in zip(host, evals_t):
+                h.copy_(t)
+            torch.cuda.synchronize()
+            h2d = sum(h.numel() * 4 for h in host)
+
+            def e2e_step():
+                for h, t in zip(host, evals_t):
+                    t.copy_(h, non_blocking=True)
+                return step()  # roots come back to the host inside commit (32 B D2H per tree)
+
+            e2e_step()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            f1.record(stream)
+            barrier()
+            ems = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n_rows / (float(ems.item()) / args.e2e_steps * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32 * len(tree_cols), "steps": args.e2e_steps}
+            del host
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as orc
+        sample = min(args.cpu_sample_cols, total_cols)
+        tcpu = cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample)
+        cpu_baseline = {"value": n_rows / (tcpu * total_cols / sample), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                        "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle, {tcpu:.1f} s), scaled linearly in columns"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 (M31)", "data": "synthetic", "config": workload_config(args, tree_cols),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "stages": stages, "roots": [r.hex()[:16] for r in roots]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def lib_eval(ctx, coeffs, log_blowup, out):
+    """evaluate into an existing batch (no allocation inside the timed breakdown)."""
+    import ctypes as C
+    import nexus_zkvm_b200 as nb
+    ctx._chk(nb.lib().nb200_evaluate(ctx._h, coeffs._h, C.c_uint32(log_blowup), out._h))
+
+
+if __name__ == "__main__":
+    main()

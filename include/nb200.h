@@ -1,0 +1,120 @@
+/* nb200.h — C ABI of libnexus_b200.so: the B200 (sm_100a) STARK proving backend that stands in for
+ * Stwo's `SimdBackend` behind the Nexus zkVM prover.
+ *
+ * The reference has no FFI: its boundary is the Rust type parameter `SimdBackend` in
+ *   CommitmentSchemeProver::<SimdBackend, Blake2sMerkleChannel>::new   prover/src/machine.rs:202-203
+ *   tree_builder.extend_evals(..) / commit(..)                         prover/src/machine.rs:208-263
+ *   stwo::prover::prove::<SimdBackend, Blake2sMerkleChannel>           prover/src/machine.rs:286-290
+ *   (same surface in prover2/machine/src/prove.rs:53-128).
+ * Each entry point below names the Stwo backend-trait method (and the reference call site) it replaces.
+ * A Rust shim `struct CudaBackend;` implementing ColumnOps/PolyOps/MerkleOps/QuotientOps/FriOps/
+ * AccumulationOps/GrindOps by calling these functions is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns nb200_status (0 = OK); no exceptions cross the ABI; host buffers are
+ * only borrowed for the duration of a call; a ctx is single-threaded (one ctx per host thread / per GPU).
+ * All field elements are canonical M31 values as uint32_t in [0, 2^31-1); a QM31 is 4 consecutive uint32_t;
+ * hashes are 32 raw bytes.  Columns are column-major: one contiguous uint32_t[2^log_size] per column, in
+ * bit-reversed circle-domain order (the order `finalize_columns` produces, prover/src/trace/utils.rs:94-106).
+ */
+#ifndef NB200_H
+#define NB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int nb200_status;
+enum {
+  NB200_OK = 0,
+  NB200_ERR_CUDA = 1,      /* a CUDA runtime call failed (see nb200_last_error) */
+  NB200_ERR_ARG = 2,       /* invalid argument */
+  NB200_ERR_NO_DEVICE = 3, /* no CUDA device: the product path never falls back to the CPU */
+  NB200_ERR_OOM = 4,
+  NB200_ERR_CONSTRAINTS = 5, /* ProvingError::ConstraintsNotSatisfied (prover/src/lib.rs:24-31) */
+  NB200_ERR_STATE = 6
+};
+
+typedef struct nb200_ctx nb200_ctx;   /* one GPU: device, stream, twiddle cache, transcript flavour   */
+typedef struct nb200_cols nb200_cols; /* a batch of n_cols device columns of one log_size, contiguous */
+typedef struct nb200_tree nb200_tree; /* a device Merkle tree (all layers)                            */
+
+/* ---- context -------------------------------------------------------------------------------------- */
+nb200_status nb200_ctx_create(int device, nb200_ctx** out);
+void nb200_ctx_destroy(nb200_ctx*);
+const char* nb200_last_error(nb200_ctx*); /* also valid with ctx == NULL for create failures */
+/* run all work of this ctx on an externally owned cudaStream_t (e.g. torch's current stream) */
+nb200_status nb200_ctx_set_stream(nb200_ctx*, void* cuda_stream);
+nb200_status nb200_sync(nb200_ctx*);
+/* transcript-affecting variants (see DESIGN.md "parity risk switches"); defaults 0,0,0 */
+nb200_status nb200_set_flavor(nb200_ctx*, int merkle_hash, int draw_domain_sep, int pow_variant);
+/* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
+uint64_t nb200_launch_count(nb200_ctx*);
+
+/* ---- columns: ColumnOps / BaseColumn (prover/src/trace/trace_builder.rs:156-164) -------------------- */
+nb200_status nb200_cols_alloc(nb200_ctx*, size_t n_cols, uint32_t log_size, nb200_cols** out);
+/* non-owning view over caller-owned device memory (n_cols x 2^log_size words, column-major), e.g. a torch tensor */
+nb200_status nb200_cols_from_device(nb200_ctx*, void* device_ptr, size_t n_cols, uint32_t log_size, nb200_cols** out);
+void nb200_cols_free(nb200_ctx*, nb200_cols*);
+size_t nb200_cols_count(const nb200_cols*);
+uint32_t nb200_cols_log_size(const nb200_cols*);
+void* nb200_cols_device_ptr(const nb200_cols*); /* column c starts at ptr + c * 2^log_size words */
+/* host (n x 2^log_size, row = one column) -> device columns [first, first+n).
+ * coset_order != 0: the host data is in trace (coset) order and the device applies
+ * coset_order_to_circle_domain_order + bit_reverse_column (prover/src/trace/utils.rs:94-106,
+ * utils_external.rs:24-39) — SURVEY §8(f1). */
+nb200_status nb200_cols_upload(nb200_ctx*, nb200_cols*, size_t first, size_t n, const uint32_t* host, int coset_order);
+nb200_status nb200_cols_download(nb200_ctx*, const nb200_cols*, size_t first, size_t n, uint32_t* host);
+/* device-to-device: reorder columns already on the device from coset order (in place) */
+nb200_status nb200_cols_finalize_order(nb200_ctx*, nb200_cols*);
+
+/* ---- PolyOps (stwo prover/poly/circle/ops.rs) ------------------------------------------------------- */
+/* PolyOps::precompute_twiddles(CanonicCoset(max_domain_log).circle_domain().half_coset)
+ * — prover/src/machine.rs:186-194.  Idempotent; larger requests replace the cache. */
+nb200_status nb200_twiddles_prepare(nb200_ctx*, uint32_t max_domain_log);
+/* domain log the cached bank was built for (0 = none) */
+uint32_t nb200_twiddles_domain_log(nb200_ctx*);
+/* download the twiddle / inverse-twiddle buffers (each 2^(nb200_twiddles_domain_log-1) words) — test hook */
+nb200_status nb200_twiddles_download(nb200_ctx*, uint32_t* tw, uint32_t* itw);
+/* PolyOps::interpolate_columns: Circle iFFT in place, evaluations on CanonicCoset(log).circle_domain()
+ * (bit-reversed) -> coefficients.   Called by TreeBuilder::extend_evals, prover/src/machine.rs:209-215. */
+nb200_status nb200_interpolate(nb200_ctx*, nb200_cols* cols);
+/* PolyOps::evaluate_polynomials: Circle FFT of the zero-extended coefficients onto
+ * CanonicCoset(log+log_blowup).circle_domain() — the LDE inside TreeBuilder::commit, machine.rs:228.
+ * `out` must be a batch of the same column count and log_size + log_blowup. */
+nb200_status nb200_evaluate(nb200_ctx*, const nb200_cols* coeffs, uint32_t log_blowup, nb200_cols* out);
+/* PolyOps::eval_at_point for every column of a batch at n_points QM31 circle points:
+ * points = n_points x {x[4], y[4]}; out = n_cols x n_points x QM31 (column-major by column). */
+nb200_status nb200_eval_at_points(nb200_ctx*, const nb200_cols* coeffs, const uint32_t* points_xy, size_t n_points, uint32_t* out_qm31);
+
+/* ---- MerkleOps<Blake2sMerkleHasher> (stwo prover/vcs/prover.rs, core/vcs/blake2_merkle.rs) ----------- */
+/* MerkleProver::commit over any mix of batches (sorted by column length, stable, as upstream):
+ * node = H(left || right || values of the columns of this layer's size at this row). */
+nb200_status nb200_merkle_commit(nb200_ctx*, const nb200_cols* const* batches, size_t n_batches, nb200_tree** out, uint8_t root[32]);
+void nb200_tree_free(nb200_ctx*, nb200_tree*);
+uint32_t nb200_tree_log_size(const nb200_tree*);
+/* download one layer (log_size 0 = root layer): 32 * 2^layer_log bytes — test hook */
+nb200_status nb200_tree_layer_download(nb200_ctx*, const nb200_tree*, uint32_t layer_log, uint8_t* out);
+/* MerkleProver::decommit.  queries: for k < n_sizes, q_log_sizes[k] with q_counts[k] sorted positions taken
+ * consecutively from q_positions.  Outputs are malloc'ed by the library; free with nb200_free. */
+nb200_status nb200_merkle_decommit(nb200_ctx*, const nb200_tree*, const nb200_cols* const* batches, size_t n_batches,
+                                   const uint32_t* q_log_sizes, const uint64_t* q_counts, const uint64_t* q_positions, size_t n_sizes,
+                                   uint32_t** queried_values, size_t* n_queried,
+                                   uint8_t** hash_witness, size_t* n_hashes,
+                                   uint32_t** column_witness, size_t* n_column_witness);
+void nb200_free(void*);
+
+/* ---- fused commitment: TreeBuilder::extend_evals + commit (machine.rs:208-263) ---------------------- */
+/* In: evaluation batches (read only).  Out, per batch: the coefficient batch (interpolate) and the LDE batch
+ * (log_size + log_blowup); coeffs_io[b] / lde_io[b] may be NULL (allocated by the library, owned by the
+ * caller afterwards) or caller-provided batches of the right shape (reused across proofs).  Also the Merkle
+ * tree over all LDE columns and its root.  This is the unit bench.py times. */
+nb200_status nb200_commit_evals(nb200_ctx*, const nb200_cols* const* eval_batches, size_t n_batches, uint32_t log_blowup,
+                                nb200_cols** coeffs_io /* n_batches */, nb200_cols** lde_io /* n_batches */,
+                                nb200_tree** tree_out, uint8_t root[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NB200_H */

@@ -1,0 +1,260 @@
+// C ABI of libnexus_b200.so (see include/nb200.h).  No CPU fallback anywhere: without a CUDA device
+// nb200_ctx_create fails with NB200_ERR_NO_DEVICE.
+#include "common.cuh"
+#include "circle_host.h"
+#include <cstdlib>
+#include <cstring>
+
+namespace nb {
+std::string& global_err() { static std::string e; return e; }
+nb200_status merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const std::vector<ColRef>& cols_in,
+                             const std::vector<std::pair<u32, std::vector<u64>>>& queries,
+                             std::vector<u32>& queried_values, std::vector<uint8_t>& hash_witness, std::vector<u32>& column_witness);
+nb200_status eval_at_points(nb200_ctx* ctx, const u32* coeffs, size_t n_cols, u32 log_size, const u32* points_xy, size_t n_points, u32* out_qm31);
+}  // namespace nb
+using namespace nb;
+
+extern "C" {
+
+nb200_status nb200_ctx_create(int device, nb200_ctx** out) {
+  if (!out) return NB200_ERR_ARG;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    global_err() = std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                   "); libnexus_b200 has no CPU fallback";
+    return NB200_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) { global_err() = "device index out of range"; return NB200_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { global_err() = cudaGetErrorString(e); return NB200_ERR_CUDA; }
+  nb200_ctx* ctx = new nb200_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { global_err() = cudaGetErrorString(e); delete ctx; return NB200_ERR_CUDA; }
+  ctx->own_stream = true;
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  *out = ctx;
+  return NB200_OK;
+}
+
+void nb200_ctx_destroy(nb200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->tw.d_tw) cudaFree(ctx->tw.d_tw);
+  if (ctx->tw.d_itw) cudaFree(ctx->tw.d_itw);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* nb200_last_error(nb200_ctx* ctx) { return ctx ? ctx->err.c_str() : global_err().c_str(); }
+
+nb200_status nb200_ctx_set_stream(nb200_ctx* ctx, void* s) {
+  if (!ctx) return NB200_ERR_ARG;
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return NB200_OK;
+}
+
+nb200_status nb200_sync(nb200_ctx* ctx) {
+  if (!ctx) return NB200_ERR_ARG;
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NB200_OK;
+}
+
+nb200_status nb200_set_flavor(nb200_ctx* ctx, int merkle_hash, int draw_domain_sep, int pow_variant) {
+  if (!ctx) return NB200_ERR_ARG;
+  NB_ARG(ctx, (merkle_hash == 0 || merkle_hash == 1) && (draw_domain_sep == 0 || draw_domain_sep == 1) && (pow_variant == 0 || pow_variant == 1), "bad flavor");
+  ctx->merkle_hash = merkle_hash; ctx->draw_domain_sep = draw_domain_sep; ctx->pow_variant = pow_variant;
+  return NB200_OK;
+}
+
+uint64_t nb200_launch_count(nb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- columns ----
+nb200_status nb200_cols_alloc(nb200_ctx* ctx, size_t n_cols, uint32_t log_size, nb200_cols** out) {
+  if (!ctx || !out) return NB200_ERR_ARG;
+  NB_ARG(ctx, log_size <= 30, "cols_alloc: log_size too large");
+  nb200_cols* c = new nb200_cols();
+  c->ctx = ctx; c->n_cols = n_cols; c->log_size = log_size;
+  size_t bytes = (n_cols << log_size) * 4;
+  if (bytes) {
+    cudaError_t e = dmalloc(ctx, (void**)&c->d, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); delete c; return set_err(ctx, NB200_ERR_OOM, std::string("cols_alloc: ") + cudaGetErrorString(e)); }
+  }
+  *out = c;
+  return NB200_OK;
+}
+nb200_status nb200_cols_from_device(nb200_ctx* ctx, void* device_ptr, size_t n_cols, uint32_t log_size, nb200_cols** out) {
+  if (!ctx || !out) return NB200_ERR_ARG;
+  NB_ARG(ctx, device_ptr != nullptr && log_size <= 30, "cols_from_device: bad arguments");
+  nb200_cols* c = new nb200_cols();
+  c->ctx = ctx; c->n_cols = n_cols; c->log_size = log_size; c->d = (uint32_t*)device_ptr; c->owns = false;
+  *out = c;
+  return NB200_OK;
+}
+void nb200_cols_free(nb200_ctx*, nb200_cols* c) {
+  if (!c) return;
+  if (c->owns && c->d) dfree(c->ctx, c->d);
+  delete c;
+}
+size_t nb200_cols_count(const nb200_cols* c) { return c ? c->n_cols : 0; }
+uint32_t nb200_cols_log_size(const nb200_cols* c) { return c ? c->log_size : 0; }
+void* nb200_cols_device_ptr(const nb200_cols* c) { return c ? c->d : nullptr; }
+
+nb200_status nb200_cols_upload(nb200_ctx* ctx, nb200_cols* c, size_t first, size_t n, const uint32_t* host, int coset_order) {
+  if (!ctx || !c) return NB200_ERR_ARG;
+  NB_ARG(ctx, first + n <= c->n_cols, "cols_upload: range");
+  if (n == 0) return NB200_OK;
+  size_t bytes = (n << c->log_size) * 4;
+  if (!coset_order) {
+    NB_CUDA(ctx, cudaMemcpyAsync(c->col(first), host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+  }
+  u32* tmp = nullptr;
+  NB_CUDA(ctx, cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  nb200_status st = NB200_OK;
+  if (e != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e));
+  if (st == NB200_OK) st = reorder_coset_to_bitrev(ctx, tmp, c->col(first), n, c->log_size);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  return st;
+}
+nb200_status nb200_cols_download(nb200_ctx* ctx, const nb200_cols* c, size_t first, size_t n, uint32_t* host) {
+  if (!ctx || !c) return NB200_ERR_ARG;
+  NB_ARG(ctx, first + n <= c->n_cols, "cols_download: range");
+  if (n == 0) return NB200_OK;
+  NB_CUDA(ctx, cudaMemcpyAsync(host, c->col(first), (n << c->log_size) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NB200_OK;
+}
+nb200_status nb200_cols_finalize_order(nb200_ctx* ctx, nb200_cols* c) {
+  if (!ctx || !c) return NB200_ERR_ARG;
+  size_t bytes = (c->n_cols << c->log_size) * 4;
+  if (!bytes) return NB200_OK;
+  u32* tmp = nullptr;
+  NB_CUDA(ctx, cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, c->d, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  nb200_status st = e == cudaSuccess ? reorder_coset_to_bitrev(ctx, tmp, c->d, c->n_cols, c->log_size) : set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e));
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  return st;
+}
+
+// ---- PolyOps ----
+nb200_status nb200_twiddles_prepare(nb200_ctx* ctx, uint32_t max_domain_log) {
+  if (!ctx) return NB200_ERR_ARG;
+  return twiddles_prepare(ctx, max_domain_log);
+}
+uint32_t nb200_twiddles_domain_log(nb200_ctx* ctx) { return (ctx && ctx->tw.d_tw) ? ctx->tw.half_log + 1 : 0; }
+nb200_status nb200_twiddles_download(nb200_ctx* ctx, uint32_t* tw, uint32_t* itw) {
+  if (!ctx) return NB200_ERR_ARG;
+  NB_ARG(ctx, ctx->tw.d_tw, "twiddles not prepared");
+  size_t bytes = ((size_t)4) << ctx->tw.half_log;
+  NB_CUDA(ctx, cudaMemcpyAsync(tw, ctx->tw.d_tw, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaMemcpyAsync(itw, ctx->tw.d_itw, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NB200_OK;
+}
+nb200_status nb200_interpolate(nb200_ctx* ctx, nb200_cols* c) {
+  if (!ctx || !c) return NB200_ERR_ARG;
+  if (c->log_size >= 1) NB_TRY(twiddles_prepare(ctx, c->log_size));
+  return fft_interpolate(ctx, c->d, c->d, c->n_cols, c->log_size);
+}
+nb200_status nb200_evaluate(nb200_ctx* ctx, const nb200_cols* coeffs, uint32_t log_blowup, nb200_cols* out) {
+  if (!ctx || !coeffs || !out) return NB200_ERR_ARG;
+  NB_ARG(ctx, out->n_cols == coeffs->n_cols && out->log_size == coeffs->log_size + log_blowup, "evaluate: output batch shape");
+  if (out->log_size >= 1) NB_TRY(twiddles_prepare(ctx, out->log_size));
+  return fft_evaluate(ctx, coeffs->d, coeffs->log_size, out->d, out->log_size, coeffs->n_cols);
+}
+nb200_status nb200_eval_at_points(nb200_ctx* ctx, const nb200_cols* coeffs, const uint32_t* points_xy, size_t n_points, uint32_t* out_qm31) {
+  if (!ctx || !coeffs) return NB200_ERR_ARG;
+  return eval_at_points(ctx, coeffs->d, coeffs->n_cols, coeffs->log_size, points_xy, n_points, out_qm31);
+}
+
+// ---- MerkleOps ----
+static void collect_cols(const nb200_cols* const* batches, size_t n_batches, std::vector<ColRef>& cols) {
+  for (size_t b = 0; b < n_batches; ++b)
+    for (size_t c = 0; c < batches[b]->n_cols; ++c) cols.push_back(ColRef{batches[b]->col(c), batches[b]->log_size});
+}
+nb200_status nb200_merkle_commit(nb200_ctx* ctx, const nb200_cols* const* batches, size_t n_batches, nb200_tree** out, uint8_t root[32]) {
+  if (!ctx || !out) return NB200_ERR_ARG;
+  std::vector<ColRef> cols;
+  collect_cols(batches, n_batches, cols);
+  NB_TRY(merkle_commit(ctx, cols, out));
+  if (root) memcpy(root, (*out)->root, 32);
+  return NB200_OK;
+}
+void nb200_tree_free(nb200_ctx*, nb200_tree* t) {
+  if (!t) return;
+  if (t->d_pool) dfree(t->ctx, t->d_pool);
+  delete t;
+}
+uint32_t nb200_tree_log_size(const nb200_tree* t) { return t ? t->max_log : 0; }
+nb200_status nb200_tree_layer_download(nb200_ctx* ctx, const nb200_tree* t, uint32_t layer_log, uint8_t* out) {
+  if (!ctx || !t) return NB200_ERR_ARG;
+  NB_ARG(ctx, layer_log <= t->max_log, "tree layer out of range");
+  NB_CUDA(ctx, cudaMemcpyAsync(out, t->layer[layer_log], (size_t)32 << layer_log, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NB200_OK;
+}
+static void* dup_bytes(const void* p, size_t n) { void* r = malloc(n ? n : 1); if (n) memcpy(r, p, n); return r; }
+nb200_status nb200_merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const nb200_cols* const* batches, size_t n_batches,
+                                   const uint32_t* q_log_sizes, const uint64_t* q_counts, const uint64_t* q_positions, size_t n_sizes,
+                                   uint32_t** queried_values, size_t* n_queried, uint8_t** hash_witness, size_t* n_hashes,
+                                   uint32_t** column_witness, size_t* n_column_witness) {
+  if (!ctx || !tree) return NB200_ERR_ARG;
+  std::vector<ColRef> cols;
+  collect_cols(batches, n_batches, cols);
+  std::vector<std::pair<u32, std::vector<u64>>> queries;
+  size_t off = 0;
+  for (size_t k = 0; k < n_sizes; ++k) {
+    queries.push_back({q_log_sizes[k], std::vector<u64>(q_positions + off, q_positions + off + q_counts[k])});
+    off += q_counts[k];
+  }
+  std::vector<u32> qv, cw; std::vector<uint8_t> hw;
+  NB_TRY(merkle_decommit(ctx, tree, cols, queries, qv, hw, cw));
+  *queried_values = (uint32_t*)dup_bytes(qv.data(), qv.size() * 4); *n_queried = qv.size();
+  *hash_witness = (uint8_t*)dup_bytes(hw.data(), hw.size()); *n_hashes = hw.size() / 32;
+  *column_witness = (uint32_t*)dup_bytes(cw.data(), cw.size() * 4); *n_column_witness = cw.size();
+  return NB200_OK;
+}
+void nb200_free(void* p) { free(p); }
+
+// ---- fused commitment ----
+nb200_status nb200_commit_evals(nb200_ctx* ctx, const nb200_cols* const* eval_batches, size_t n_batches, uint32_t log_blowup,
+                                nb200_cols** coeffs_io, nb200_cols** lde_io, nb200_tree** tree_out, uint8_t root[32]) {
+  if (!ctx || !coeffs_io || !lde_io || !tree_out) return NB200_ERR_ARG;
+  u32 max_log = 0;
+  for (size_t b = 0; b < n_batches; ++b) max_log = std::max(max_log, eval_batches[b]->log_size + log_blowup);
+  if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
+  std::vector<ColRef> cols;
+  for (size_t b = 0; b < n_batches; ++b) {
+    const nb200_cols* ev = eval_batches[b];
+    if (!coeffs_io[b]) NB_TRY(nb200_cols_alloc(ctx, ev->n_cols, ev->log_size, &coeffs_io[b]));
+    if (!lde_io[b]) NB_TRY(nb200_cols_alloc(ctx, ev->n_cols, ev->log_size + log_blowup, &lde_io[b]));
+    nb200_cols *co = coeffs_io[b], *lde = lde_io[b];
+    NB_ARG(ctx, co->n_cols == ev->n_cols && co->log_size == ev->log_size, "commit_evals: coefficient batch shape");
+    NB_ARG(ctx, lde->n_cols == ev->n_cols && lde->log_size == ev->log_size + log_blowup, "commit_evals: LDE batch shape");
+    NB_TRY(fft_interpolate(ctx, ev->d, co->d, ev->n_cols, ev->log_size));
+    NB_TRY(fft_evaluate(ctx, co->d, co->log_size, lde->d, lde->log_size, ev->n_cols));
+    for (size_t c = 0; c < lde->n_cols; ++c) cols.push_back(ColRef{lde->col(c), lde->log_size});
+  }
+  NB_TRY(merkle_commit(ctx, cols, tree_out));
+  if (root) memcpy(root, (*tree_out)->root, 32);
+  return NB200_OK;
+}
+
+}  // extern "C"

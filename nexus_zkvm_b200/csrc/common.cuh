@@ -1,0 +1,105 @@
+// Shared definitions of the product library (context, device column batches, trees, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/nb200.h"
+#include "m31.cuh"
+
+namespace nb {
+
+struct TwiddleBank {
+  u32 half_log = 0;       // log size k of the root half coset; buffers hold 2^k words
+  u32* d_tw = nullptr;    // x-coordinates, layer l at offset 2^k - 2^(k-l), bit-reversed within the layer
+  u32* d_itw = nullptr;   // element-wise inverses
+};
+
+}  // namespace nb
+
+struct nb200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  nb::TwiddleBank tw;
+  int merkle_hash = 0, draw_domain_sep = 0, pow_variant = 0;
+  uint64_t launches = 0;
+  // scratch for small device->host transfers
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+};
+
+struct nb200_cols {
+  nb200_ctx* ctx = nullptr;
+  size_t n_cols = 0;
+  uint32_t log_size = 0;
+  uint32_t* d = nullptr;  // n_cols * 2^log_size words, column-major
+  bool owns = true;
+  size_t col_len() const { return (size_t)1 << log_size; }
+  uint32_t* col(size_t c) const { return d + c * col_len(); }
+};
+
+struct nb200_tree {
+  nb200_ctx* ctx = nullptr;
+  uint32_t max_log = 0;
+  uint8_t* d_pool = nullptr;              // all layers, root first
+  std::vector<uint8_t*> layer;            // layer[l] -> 32 * 2^l bytes
+  uint8_t root[32];
+};
+
+namespace nb {
+
+inline nb200_status set_err(nb200_ctx* ctx, nb200_status st, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return st;
+}
+std::string& global_err();
+
+#define NB_CUDA(ctx, call)                                                                                   \
+  do {                                                                                                       \
+    cudaError_t _e = (call);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      return nb::set_err(ctx, _e == cudaErrorMemoryAllocation ? NB200_ERR_OOM : NB200_ERR_CUDA,              \
+                         std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+    }                                                                                                        \
+  } while (0)
+
+#define NB_LAUNCH_CHECK(ctx)                                                                                 \
+  do {                                                                                                       \
+    (ctx)->launches += 1;                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                                     \
+    if (_e != cudaSuccess)                                                                                   \
+      return nb::set_err(ctx, NB200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define NB_ARG(ctx, cond, msg)                                                   \
+  do {                                                                           \
+    if (!(cond)) return nb::set_err(ctx, NB200_ERR_ARG, std::string(msg));       \
+  } while (0)
+
+#define NB_TRY(expr)                          \
+  do {                                        \
+    nb200_status _s = (expr);                 \
+    if (_s != NB200_OK) return _s;            \
+  } while (0)
+
+// Stream-ordered device allocation from the device's default memory pool (release threshold raised at ctx
+// creation, so steady-state alloc/free never reaches the driver).
+inline cudaError_t dmalloc(nb200_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream); }
+inline void dfree(nb200_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+// ---- internal launchers (implemented in the .cu files) ----
+nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log);
+// Circle iFFT in place over a batch (evaluations -> coefficients)
+nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
+// Circle FFT: coefficients (src, log src_log) zero-extended to dst (log dst_log); src may equal dst if logs match
+nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols);
+nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
+
+struct ColRef { const u32* d; u32 log_size; };
+nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out);
+
+}  // namespace nb

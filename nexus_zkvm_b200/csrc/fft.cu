@@ -1,0 +1,326 @@
+// Circle FFT / iFFT over M31 for batches of columns (PolyOps::interpolate / PolyOps::evaluate).
+// Replaces the SimdBackend `ifft` / `rfft` reached from TreeBuilder::extend_evals and TreeBuilder::commit at
+// /root/reference prover/src/machine.rs:208-263 (and prover2/machine/src/prove.rs:70-105).
+//
+// Algorithm (identical butterfly network to stwo's CPU backend so results are bit-exact):
+//   values are in bit-reversed circle-domain order; layer i pairs indices that differ in bit i with
+//   twiddle index h = idx >> (i+1); layer 0 uses the circle (y) twiddles derived from the first line layer
+//   ([x, y] -> [y, -y, -x, x]), layers >= 1 use line (x) twiddles; interpolate runs layers 0..n-1 with
+//   ibutterfly and scales by 2^-n, evaluate runs n-1..0 with butterfly on zero-extended coefficients.
+//
+// Kernel structure (HBM-bound integer work, no tensor cores):
+//   A transform of 2^n is split into passes of <= 13 layers.  A pass owns a contiguous range of layers
+//   [lo, lo+L); each CTA stages a tile of 2^T words (2^L "rows" x 2^W contiguous words, W = T-L) of CB columns
+//   into shared memory with coalesced accesses, runs the L layers there in rounds of <= 4 layers (every
+//   thread holds 16 words in registers: a radix-16 butterfly network per round), and writes the tile back.
+//   Twiddles of a round are loaded once into registers and reused for the CB columns of the CTA.
+//   Shared memory is XOR-swizzled (s ^ ((s >> 4) & 31)) which makes every round and the staging
+//   conflict-free (verified exhaustively by tests/test_layout.py).
+#include "common.cuh"
+#include "circle_host.h"
+
+namespace nb {
+
+struct FftPass {
+  const u32* src;     // source columns (column c at src + c*src_stride); zero-extended beyond src_len
+  u32* dst;           // destination columns
+  size_t src_stride, dst_stride;
+  size_t src_len;     // valid words per source column
+  const u32* tw;      // twiddle (or inverse twiddle) bank
+  u32 tw_len;         // bank length (2^k)
+  u32 n_cols;
+  u32 n;              // log size of the transform
+  u32 lo;             // first layer of this pass
+  u32 T, W;           // tile log, width log (L = T - W layers)
+  u32 cb;             // columns per CTA
+  u32 scale;          // multiply outputs by this (interpolate last pass) if apply_scale
+  u32 apply_scale;
+};
+
+__device__ __forceinline__ u32 swz(u32 s) { return s ^ ((s >> 4) & 31u); }
+
+__device__ __forceinline__ void butterfly(u32& v0, u32& v1, u32 t) {
+  u32 tmp = m31_mul(v1, t);
+  v1 = m31_sub(v0, tmp);
+  v0 = m31_add(v0, tmp);
+}
+__device__ __forceinline__ void ibutterfly(u32& v0, u32& v1, u32 it) {
+  u32 tmp = v0;
+  v0 = m31_add(tmp, v1);
+  v1 = m31_mul(m31_sub(tmp, v1), it);
+}
+
+// twiddle of layer i (>= 1) at index h for a transform of log size n
+__device__ __forceinline__ u32 line_tw(const u32* __restrict__ tw, u32 tw_len, u32 n, u32 i, u32 h) {
+  return __ldg(tw + (tw_len - (1u << (n - i)) + h));
+}
+// circle twiddle (layer 0) at index h: from the first line layer, [x, y] -> [y, -y, -x, x]
+__device__ __forceinline__ u32 circle_tw(const u32* __restrict__ tw, u32 tw_len, u32 n, u32 h) {
+  const u32* l1 = tw + (tw_len - (1u << (n - 1)));
+  u32 q = h >> 2, r = h & 3u;
+  u32 x = __ldg(l1 + 2 * q), y = __ldg(l1 + 2 * q + 1);
+  u32 v = (r < 2) ? y : x;
+  return (r == 1 || r == 2) ? (P31 - v) : v;
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
+  extern __shared__ u32 sm[];
+  const u32 T = p.T, W = p.W, L = T - W, lo = p.lo, n = p.n;
+  const u32 nthreads = blockDim.x;  // 2^(T-4)
+  const u32 tid = threadIdx.x;
+  const u32 tile = blockIdx.x;
+  const u32 mid_bits = lo > W ? lo - W : 0;  // lo == 0 implies W == 0
+  const u32 tile_mid = tile & ((1u << mid_bits) - 1u);
+  const u32 tile_hi = tile >> mid_bits;
+  const size_t gbase = ((size_t)tile_hi << (lo + L)) | ((size_t)tile_mid << W);
+  const u32 wmask = (1u << W) - 1u;
+  const u32 col0 = blockIdx.y * p.cb;
+  const u32 ncb = min(p.cb, p.n_cols - col0);
+  const u32 tile_words = 1u << T;
+
+  // ---- stage in: coalesced global -> swizzled shared
+  for (u32 c = 0; c < ncb; ++c) {
+    const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
+    u32* smc = sm + ((size_t)c << T);
+    for (u32 s = tid; s < tile_words; s += nthreads) {
+      size_t g = gbase | ((size_t)(s >> W) << lo) | (s & wmask);
+      u32 v = g < p.src_len ? __ldg(scol + g) : 0u;
+      smc[swz(s)] = v;
+    }
+  }
+  __syncthreads();
+
+  const u32 nfull = L >> 2, rem = L & 3u;
+  const u32 nrounds = nfull + (rem ? 1u : 0u);
+  for (u32 rr = 0; rr < nrounds; ++rr) {
+    const u32 ri = INV ? rr : nrounds - 1 - rr;
+    u32 b, jlo;
+    if (ri < nfull) { b = W + 4 * ri; jlo = 0; } else { b = T - 4; jlo = 4 - rem; }
+    const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
+    // twiddles of this round: layer j (register bit) <-> global layer i = lo + b + j - W
+    u32 tw[15];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((u32)j >= jlo) {
+        const u32 i = lo + b + j - W;
+        const u32 hbase = ((tile_hi << (L - (b + j - W) - 1)) | (tau_hi << (3 - j)));
+#pragma unroll
+        for (int kk = 0; kk < (8 >> j); ++kk) {
+          const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + kk;
+          tw[off] = (i == 0) ? circle_tw(p.tw, p.tw_len, n, hbase + kk) : line_tw(p.tw, p.tw_len, n, i, hbase + kk);
+        }
+      }
+    }
+    const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
+    for (u32 c = 0; c < ncb; ++c) {
+      u32* smc = sm + ((size_t)c << T);
+      u32 v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = smc[swz(sbase | ((u32)k << b))];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = INV ? jj : 3 - jj;
+        if ((u32)j >= jlo) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
+            const int k1 = k0 | (1 << j);
+            const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
+            if (INV) ibutterfly(v[k0], v[k1], tw[off]);
+            else butterfly(v[k0], v[k1], tw[off]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) smc[swz(sbase | ((u32)k << b))] = v[k];
+    }
+    __syncthreads();
+  }
+
+  // ---- stage out
+  for (u32 c = 0; c < ncb; ++c) {
+    u32* __restrict__ dcol = p.dst + (size_t)(col0 + c) * p.dst_stride;
+    const u32* smc = sm + ((size_t)c << T);
+    for (u32 s = tid; s < tile_words; s += nthreads) {
+      size_t g = gbase | ((size_t)(s >> W) << lo) | (s & wmask);
+      u32 v = smc[swz(s)];
+      if (p.apply_scale) v = m31_mul(v, p.scale);
+      dcol[g] = v;
+    }
+  }
+}
+
+// Generic small transform (n <= 12): one CTA per column, whole column in shared memory, layer by layer.
+struct FftSmall {
+  const u32* src; u32* dst; size_t src_stride, dst_stride, src_len;
+  const u32* tw; u32 tw_len; u32 n_cols, n;
+  u32 y0;      // n <= 2: (inverse of) y of half_coset.initial
+  u32 scale, apply_scale;
+};
+template <bool INV>
+__global__ void fft_small_kernel(const FftSmall p) {
+  extern __shared__ u32 sm[];
+  const u32 n = p.n, len = 1u << n, half = len >> 1;
+  const u32 c = blockIdx.x;
+  const u32* __restrict__ scol = p.src + (size_t)c * p.src_stride;
+  u32* __restrict__ dcol = p.dst + (size_t)c * p.dst_stride;
+  for (u32 s = threadIdx.x; s < len; s += blockDim.x) sm[s] = s < p.src_len ? scol[s] : 0u;
+  __syncthreads();
+  for (u32 ll = 0; ll < n; ++ll) {
+    const u32 i = INV ? ll : n - 1 - ll;
+    for (u32 idx = threadIdx.x; idx < half; idx += blockDim.x) {
+      u32 h = idx >> i, l = idx & ((1u << i) - 1u);
+      u32 i0 = (h << (i + 1)) + l, i1 = i0 + (1u << i);
+      u32 t;
+      if (i == 0) {
+        if (n <= 2) t = (h & 1u) ? (P31 - p.y0) : p.y0;   // n == 1: [y]; n == 2: [y, -y]
+        else t = circle_tw(p.tw, p.tw_len, n, h);
+      } else {
+        t = line_tw(p.tw, p.tw_len, n, i, h);
+      }
+      u32 a = sm[i0], b = sm[i1];
+      if (INV) ibutterfly(a, b, t); else butterfly(a, b, t);
+      sm[i0] = a; sm[i1] = b;
+    }
+    __syncthreads();
+  }
+  for (u32 s = threadIdx.x; s < len; s += blockDim.x) {
+    u32 v = sm[s];
+    if (p.apply_scale) v = m31_mul(v, p.scale);
+    dcol[s] = v;
+  }
+}
+
+// out[i] = in[src(i)]: coset order -> circle-domain order -> bit-reversed  (finalize_columns,
+// /root/reference prover/src/trace/utils.rs:94-106 + utils_external.rs:24-39)
+__global__ void reorder_kernel(const u32* __restrict__ src, u32* __restrict__ dst, u32 log_size, size_t total) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  size_t n = (size_t)1 << log_size;
+  size_t c = e >> log_size;
+  u32 i = (u32)(e & (n - 1));
+  u32 j = log_size ? (__brev(i) >> (32 - log_size)) : 0;
+  size_t half = n >> 1;
+  size_t s = j < half ? ((size_t)j << 1) : (n - 1 - (((size_t)j - half) << 1));
+  dst[e] = src[c * n + s];
+}
+
+nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size) {
+  NB_ARG(ctx, src != dst, "reorder must be out of place");
+  size_t total = n_cols << log_size;
+  if (total == 0) return NB200_OK;
+  u32 threads = 256;
+  size_t blocks = (total + threads - 1) / threads;
+  reorder_kernel<<<(u32)blocks, threads, 0, ctx->stream>>>(src, dst, log_size, total);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
+// ---- pass planning ----
+struct PassPlan { u32 lo, T, W; };
+static void plan_passes(u32 n, std::vector<PassPlan>& out) {
+  // contiguous pass over the low layers, then strided passes (tile rows x 2^W contiguous words)
+  out.clear();
+  u32 LA = n <= 13 ? n : (n >= 21 ? 13 : 12);
+  out.push_back(PassPlan{0, LA, 0});
+  u32 rest = n - LA;
+  if (rest == 0) return;
+  u32 npass = (rest + 7) / 8;
+  u32 lo = LA;
+  for (u32 k = 0; k < npass; ++k) {
+    u32 L = rest / npass + (k < rest % npass ? 1 : 0);
+    out.push_back(PassPlan{lo, 12, 12 - L});
+    lo += L;
+  }
+}
+
+template <bool INV>
+static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* src, size_t src_stride, size_t src_len,
+                                u32* dst, size_t dst_stride, size_t n_cols, u32 n, bool scale) {
+  FftPass p;
+  p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = src_len;
+  p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
+  p.tw_len = 1u << ctx->tw.half_log;
+  p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
+  p.cb = pl.T >= 13 ? 2 : 4;
+  if (p.cb > n_cols) p.cb = (u32)n_cols;
+  p.scale = 0; p.apply_scale = 0;
+  if (scale) { p.apply_scale = 1; p.scale = m31_inv((u32)(1u << n) % P31); }
+  u32 threads = 1u << (pl.T - 4);
+  size_t smem = (size_t)p.cb << (pl.T + 2);
+  dim3 grid(1u << (n - pl.T), (u32)((n_cols + p.cb - 1) / p.cb));
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[INV ? 1 : 0]) {
+    NB_CUDA(ctx, cudaFuncSetAttribute(fft_pass_kernel<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set[INV ? 1 : 0] = true;
+  }
+  fft_pass_kernel<INV><<<grid, threads, smem, ctx->stream>>>(p);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
+template <bool INV>
+static nb200_status launch_small(nb200_ctx* ctx, const u32* src, size_t src_stride, size_t src_len, u32* dst, size_t dst_stride,
+                                 size_t n_cols, u32 n, bool scale) {
+  FftSmall p;
+  p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = src_len;
+  p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
+  p.tw_len = 1u << ctx->tw.half_log;
+  p.n_cols = (u32)n_cols; p.n = n;
+  p.y0 = 0;
+  if (n >= 1 && n <= 2) {
+    u32 y = HCoset::half_odds(n - 1).at(0).y;
+    p.y0 = INV ? m31_inv(y) : y;
+  }
+  p.scale = 0; p.apply_scale = 0;
+  if (scale) { p.apply_scale = 1; p.scale = m31_inv((u32)(1u << n) % P31); }
+  u32 half = n ? (1u << (n - 1)) : 1;
+  u32 threads = half < 32 ? 32 : (half > 256 ? 256 : half);
+  size_t smem = (size_t)4 << n;
+  fft_small_kernel<INV><<<(u32)n_cols, threads, smem, ctx->stream>>>(p);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
+static const u32 SMALL_MAX_LOG = 8;
+
+nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* data, size_t n_cols, u32 n) {
+  if (n_cols == 0) return NB200_OK;
+  NB_ARG(ctx, n <= 30, "interpolate: log size too large");
+  if (n == 0) {  // constant polynomial: coeff == value
+    if (src != data) NB_CUDA(ctx, cudaMemcpyAsync(data, src, n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NB200_OK;
+  }
+  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= n, "interpolate: twiddles not prepared for this size");
+  size_t len = (size_t)1 << n;
+  if (n <= SMALL_MAX_LOG) return launch_small<true>(ctx, src, len, len, data, len, n_cols, n, true);
+  std::vector<PassPlan> plan;
+  plan_passes(n, plan);
+  for (size_t k = 0; k < plan.size(); ++k)
+    NB_TRY(launch_pass<true>(ctx, plan[k], k == 0 ? src : data, len, len, data, len, n_cols, n, k + 1 == plan.size()));
+  return NB200_OK;
+}
+
+nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 n, size_t n_cols) {
+  if (n_cols == 0) return NB200_OK;
+  NB_ARG(ctx, src_log <= n && n <= 30, "evaluate: bad sizes");
+  size_t slen = (size_t)1 << src_log, len = (size_t)1 << n;
+  if (n == 0) {
+    if (src != dst) NB_CUDA(ctx, cudaMemcpyAsync(dst, src, n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NB200_OK;
+  }
+  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= n, "evaluate: twiddles not prepared for this size");
+  NB_ARG(ctx, src != dst || src_log == n, "evaluate: in-place requires equal sizes");
+  if (n <= SMALL_MAX_LOG) return launch_small<false>(ctx, src, slen, slen, dst, len, n_cols, n, false);
+  std::vector<PassPlan> plan;
+  plan_passes(n, plan);
+  for (size_t k = plan.size(); k-- > 0;) {
+    bool first = (k + 1 == plan.size());
+    if (first) NB_TRY(launch_pass<false>(ctx, plan[k], src, slen, slen, dst, len, n_cols, n, false));
+    else NB_TRY(launch_pass<false>(ctx, plan[k], dst, len, len, dst, len, n_cols, n, false));
+  }
+  return NB200_OK;
+}
+
+}  // namespace nb

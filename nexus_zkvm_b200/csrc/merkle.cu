@@ -1,0 +1,212 @@
+// Blake2s Merkle commitment of mixed-size column sets (MerkleOps<Blake2sMerkleHasher>::commit_on_layer,
+// MerkleProver::commit / decommit).  Replaces the SimdBackend path reached from TreeBuilder::commit at
+// /root/reference prover/src/machine.rs:228,237,263 and from FRI layer commits inside stwo::prover::prove
+// (machine.rs:286-290).
+//
+// node(layer l, row r) = H( child(2r) || child(2r+1) [if a deeper layer exists] || v_c[r] for every column c of
+// length 2^l, in the stable length-descending order of the input ).  Two hash constructions are supported
+// (DESIGN.md "parity risk switches"): 0 = chained raw Blake2s compressions from the zero state (what stwo's SIMD
+// compress16 path computes), 1 = RFC 7693 Blake2s-256 of the byte string.
+//
+// Kernel: one thread per node.  A warp reads 32 consecutive rows of each column (128-byte coalesced segments);
+// 16 column words form one 64-byte message block held in registers, so no transposition is ever materialised.
+// The work is integer-ALU bound (~1.2k ops per 64-byte block), not HBM bound.
+#include "common.cuh"
+#include "blake2s.cuh"
+#include <algorithm>
+
+namespace nb {
+
+template <int VARIANT>
+__global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restrict__ prev, const u32* const* __restrict__ cols,
+                                                            u32 n_cols, u32 log_size, uint4* __restrict__ out) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= ((size_t)1 << log_size)) return;
+  u32 h[8];
+  u32 m[16];
+  u64 t = 0;
+  const u32 total_words = (prev ? 16u : 0u) + n_cols;
+  const u64 total_bytes = (u64)total_words * 4;
+  if (VARIANT == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = 0;
+  } else {
+    b2s_init(h);
+  }
+  if (prev) {
+    const uint4* p = prev + 4 * row;  // two 32-byte children = 4 x uint4
+    uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+    if (VARIANT == 0) {
+      b2s_compress(h, m, 0, 0, 0, 0);
+    } else {
+      t = 64;
+      bool last = (n_cols == 0);
+      b2s_compress(h, m, (u32)t, 0, last ? 0xFFFFFFFFu : 0u, 0);
+    }
+  } else if (VARIANT == 1 && n_cols == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = 0;
+    b2s_compress(h, m, 0, 0, 0xFFFFFFFFu, 0);
+  }
+  for (u32 c0 = 0; c0 < n_cols; c0 += 16) {
+    if (c0 + 16 <= n_cols) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m[j] = __ldg(cols[c0 + j] + row);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m[j] = (c0 + j < n_cols) ? __ldg(cols[c0 + j] + row) : 0u;
+    }
+    if (VARIANT == 0) {
+      b2s_compress(h, m, 0, 0, 0, 0);
+    } else {
+      bool last = (c0 + 16 >= n_cols);
+      t = last ? total_bytes : t + 64;
+      b2s_compress(h, m, (u32)t, (u32)(t >> 32), last ? 0xFFFFFFFFu : 0u, 0);
+    }
+  }
+  uint4* o = out + 2 * row;
+  o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, nb200_tree** out) {
+  // stable sort by length, descending (MerkleProver::commit)
+  std::vector<ColRef> cols = cols_in;
+  std::stable_sort(cols.begin(), cols.end(), [](const ColRef& a, const ColRef& b) { return a.log_size > b.log_size; });
+  u32 max_log = cols.empty() ? 0 : cols[0].log_size;
+  NB_ARG(ctx, max_log <= 30, "merkle: column too large");
+  nb200_tree* tree = new nb200_tree();
+  tree->ctx = ctx;
+  tree->max_log = max_log;
+  size_t total_nodes = ((size_t)2 << max_log) - 1;
+  cudaError_t e = dmalloc(ctx, (void**)&tree->d_pool, total_nodes * 32);
+  if (e != cudaSuccess) { delete tree; return set_err(ctx, NB200_ERR_OOM, std::string("merkle pool: ") + cudaGetErrorString(e)); }
+  tree->layer.resize(max_log + 1);
+  {
+    size_t off = 0;
+    for (u32 l = 0; l <= max_log; ++l) { tree->layer[l] = tree->d_pool + off * 32; off += (size_t)1 << l; }
+  }
+  // device array of column pointers in sorted order
+  const u32** d_ptrs = nullptr;
+  std::vector<const u32*> h_ptrs(cols.size());
+  for (size_t i = 0; i < cols.size(); ++i) h_ptrs[i] = cols[i].d;
+  if (!cols.empty()) {
+    e = dmalloc(ctx, (void**)&d_ptrs, cols.size() * sizeof(u32*));
+    if (e != cudaSuccess) { dfree(ctx, tree->d_pool); delete tree; return set_err(ctx, NB200_ERR_OOM, "merkle ptrs"); }
+    e = cudaMemcpyAsync(d_ptrs, h_ptrs.data(), cols.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { dfree(ctx, (void*)d_ptrs); dfree(ctx, tree->d_pool); delete tree; return set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  size_t ci = 0;
+  for (int l = (int)max_log; l >= 0; --l) {
+    size_t first = ci;
+    while (ci < cols.size() && cols[ci].log_size == (u32)l) ++ci;
+    u32 n_here = (u32)(ci - first);
+    const uint4* prev = (l == (int)max_log) ? nullptr : (const uint4*)tree->layer[l + 1];
+    size_t rows = (size_t)1 << l;
+    u32 threads = 128;
+    u32 blocks = (u32)((rows + threads - 1) / threads);
+    if (ctx->merkle_hash == 0)
+      merkle_layer_kernel<0><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l]);
+    else
+      merkle_layer_kernel<1><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l]);
+    ctx->launches += 1;
+  }
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tree->root, tree->layer[0], 32, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (d_ptrs) dfree(ctx, (void*)d_ptrs);
+  if (e != cudaSuccess) { dfree(ctx, tree->d_pool); delete tree; return set_err(ctx, NB200_ERR_CUDA, std::string("merkle commit: ") + cudaGetErrorString(e)); }
+  *out = tree;
+  return NB200_OK;
+}
+
+// ---- gathers used by decommit / query openings ----
+__global__ void gather_u32_kernel(const u32* const* __restrict__ addrs, size_t n, u32* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = *addrs[i];
+}
+__global__ void gather_hash_kernel(const uint4* const* __restrict__ addrs, size_t n, uint4* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { out[2 * i] = addrs[i][0]; out[2 * i + 1] = addrs[i][1]; }
+}
+
+nb200_status gather_u32(nb200_ctx* ctx, const std::vector<const u32*>& addrs, u32* host_out) {
+  if (addrs.empty()) return NB200_OK;
+  const u32** d_a = nullptr; u32* d_o = nullptr;
+  NB_CUDA(ctx, cudaMalloc(&d_a, addrs.size() * sizeof(u32*)));
+  NB_CUDA(ctx, cudaMalloc(&d_o, addrs.size() * 4));
+  NB_CUDA(ctx, cudaMemcpyAsync(d_a, addrs.data(), addrs.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
+  gather_u32_kernel<<<(u32)((addrs.size() + 255) / 256), 256, 0, ctx->stream>>>(d_a, addrs.size(), d_o);
+  NB_LAUNCH_CHECK(ctx);
+  NB_CUDA(ctx, cudaMemcpyAsync(host_out, d_o, addrs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_a); cudaFree(d_o);
+  return NB200_OK;
+}
+nb200_status gather_hash(nb200_ctx* ctx, const std::vector<const uint8_t*>& addrs, uint8_t* host_out) {
+  if (addrs.empty()) return NB200_OK;
+  const uint4** d_a = nullptr; uint4* d_o = nullptr;
+  NB_CUDA(ctx, cudaMalloc(&d_a, addrs.size() * sizeof(void*)));
+  NB_CUDA(ctx, cudaMalloc(&d_o, addrs.size() * 32));
+  NB_CUDA(ctx, cudaMemcpyAsync(d_a, addrs.data(), addrs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  gather_hash_kernel<<<(u32)((addrs.size() + 255) / 256), 256, 0, ctx->stream>>>(d_a, addrs.size(), d_o);
+  NB_LAUNCH_CHECK(ctx);
+  NB_CUDA(ctx, cudaMemcpyAsync(host_out, d_o, addrs.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_a); cudaFree(d_o);
+  return NB200_OK;
+}
+
+// MerkleProver::decommit (stwo prover/vcs/prover.rs): same walk as upstream; the hashes and column values it
+// names are fetched from the device with two gathers.
+nb200_status merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const std::vector<ColRef>& cols_in,
+                             const std::vector<std::pair<u32, std::vector<u64>>>& queries,
+                             std::vector<u32>& queried_values, std::vector<uint8_t>& hash_witness, std::vector<u32>& column_witness) {
+  std::vector<ColRef> cols = cols_in;
+  std::stable_sort(cols.begin(), cols.end(), [](const ColRef& a, const ColRef& b) { return a.log_size > b.log_size; });
+  std::vector<const u32*> val_addrs;       // in visit order
+  std::vector<uint8_t> val_is_query;       // 1 -> queried_values, 0 -> column_witness
+  std::vector<const uint8_t*> hash_addrs;
+  size_t ci = 0;
+  std::vector<u64> last_layer_queries;
+  for (int l = (int)tree->max_log; l >= 0; --l) {
+    std::vector<u64> layer_total;
+    size_t first = ci;
+    while (ci < cols.size() && cols[ci].log_size == (u32)l) ++ci;
+    const uint8_t* prev_hashes = ((u32)l < tree->max_log) ? tree->layer[l + 1] : nullptr;
+    const std::vector<u64>* lq = nullptr;
+    for (auto& q : queries) if (q.first == (u32)l) lq = &q.second;
+    size_t pq = 0, cq = 0;
+    size_t nlq = lq ? lq->size() : 0;
+    while (true) {
+      bool has_p = pq < last_layer_queries.size(), has_c = cq < nlq;
+      if (!has_p && !has_c) break;
+      u64 node;
+      if (has_p && has_c) node = std::min(last_layer_queries[pq] / 2, (*lq)[cq]);
+      else if (has_p) node = last_layer_queries[pq] / 2;
+      else node = (*lq)[cq];
+      if (prev_hashes) {
+        if (pq < last_layer_queries.size() && last_layer_queries[pq] == 2 * node) ++pq;
+        else hash_addrs.push_back(prev_hashes + 32 * (2 * node));
+        if (pq < last_layer_queries.size() && last_layer_queries[pq] == 2 * node + 1) ++pq;
+        else hash_addrs.push_back(prev_hashes + 32 * (2 * node + 1));
+      }
+      bool queried = cq < nlq && (*lq)[cq] == node;
+      if (queried) ++cq;
+      for (size_t c = first; c < ci; ++c) { val_addrs.push_back(cols[c].d + node); val_is_query.push_back(queried ? 1 : 0); }
+      layer_total.push_back(node);
+    }
+    last_layer_queries.swap(layer_total);
+  }
+  std::vector<u32> vals(val_addrs.size());
+  NB_TRY(gather_u32(ctx, val_addrs, vals.data()));
+  hash_witness.resize(hash_addrs.size() * 32);
+  NB_TRY(gather_hash(ctx, hash_addrs, hash_witness.data()));
+  queried_values.clear(); column_witness.clear();
+  for (size_t i = 0; i < vals.size(); ++i) (val_is_query[i] ? queried_values : column_witness).push_back(vals[i]);
+  return NB200_OK;
+}
+
+}  // namespace nb

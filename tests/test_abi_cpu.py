@@ -1,0 +1,53 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol that
+include/nb200.h declares, and refuses to run without a CUDA device (no CPU fallback on the product path)."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import nexus_zkvm_b200 as nb
+from nexus_zkvm_b200 import build as nb_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    return nb_build.build()
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "nb200.h"\nint main(void){return NB200_OK;}\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = C.CDLL(built)
+    syms = nb.exported_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_device(built):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(nb.Nb200Error) as ei:
+        nb.Context(0)
+    assert "no CPU fallback" in str(ei.value) or "no CUDA device" in str(ei.value)
+
+
+def test_product_sources_do_not_reference_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "nexus_zkvm_b200")):
+        if os.path.basename(root) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
