@@ -12,8 +12,10 @@ using namespace orc;
 
 static std::map<uint32_t, std::shared_ptr<TwiddleTree>>& tw_cache() { static std::map<uint32_t, std::shared_ptr<TwiddleTree>> m; return m; }
 static std::mutex tw_mu;
+static const TwiddleTree& orc_get_twiddles(uint32_t domain_log);
+namespace orc { const TwiddleTree& get_twiddles(uint32_t domain_log) { return orc_get_twiddles(domain_log); } }
 // twiddle tree whose root is the half coset of the canonic circle domain of `domain_log`
-const TwiddleTree& orc_get_twiddles(uint32_t domain_log) {
+static const TwiddleTree& orc_get_twiddles(uint32_t domain_log) {
   std::lock_guard<std::mutex> g(tw_mu);
   auto& m = tw_cache();
   // any cached bigger tree works (suffix property) but keep it simple/explicit: exact size
