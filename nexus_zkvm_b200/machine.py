@@ -1,0 +1,149 @@
+"""A Nexus-shaped synthetic machine driven through the drop-in boundary.
+
+The reference's `Machine::<C>::prove_with_extensions` (/root/reference prover/src/machine.rs:130-297) fills the trace
+with Rust chips and then drives Stwo: channel prefix -> tree 0 (preprocessed) -> tree 1 (main) -> draw lookup
+elements -> interaction trace -> mix claimed sums -> tree 2 -> stwo::prover::prove.  The chips themselves cannot be
+executed here (Rust, no toolchain), so this module provides a machine of the same *shape* that exercises every part
+of the backend surface: a wide ADD chip (byte limbs + carries, the core of prover/src/chips/instructions/i/add.rs:98-139),
+a next-row constraint on a program counter (mask offset +1, like `Pc`, prover/src/column.rs:17-19), boolean-ity
+constraints (range_bool.rs), one LogUp fraction per range-checked byte with one secure column per fraction
+(`finalize_logup`, components/mod.rs:52-54), and a second, small component (a 2^8 multiplicity table with a
+preprocessed column addressed by id, like prover/src/extensions/multiplicity.rs) so that trees hold mixed-size columns.
+With 21 lanes the column counts are 3 / 341 / 1012 — the reference's 27 / 347 / 1012.
+
+`prove(backend, ...)` is written against a small backend protocol so the very same driver runs the CUDA backend
+(nexus_zkvm_b200.prover.CudaBackend) and, in tests only, the oracle.
+"""
+import numpy as np
+
+from . import air as A
+from . import field as F
+
+P = (1 << 31) - 1
+
+
+class AddMachine:
+    def __init__(self, log_size, n_lanes=1, log_expand=2):
+        assert log_size >= 8
+        self.log_size, self.n_lanes, self.log_expand = log_size, n_lanes, log_expand
+        air = A.Air()
+        self.range256 = air.relation("Range256", 1)
+        main = air.component(log_size, log_expand)
+        is_first = main.get_preprocessed_column("IsFirst")
+        is_last = main.get_preprocessed_column("IsLast")
+        # main trace (tree 1), column order = declaration order (trace/eval.rs:31-44)
+        pc = main.next_interaction_mask(A.ORIGINAL_TRACE_IDX, [0, 1])  # like Column::Pc: [cur, next]
+        is_pad = main.next_trace_mask()
+        lanes = []
+        for _ in range(n_lanes):
+            a = [main.next_trace_mask() for _ in range(4)]
+            b = [main.next_trace_mask() for _ in range(4)]
+            c = [main.next_trace_mask() for _ in range(4)]
+            carry = [main.next_trace_mask() for _ in range(4)]
+            lanes.append((a, b, c, carry))
+        # constraints
+        main.add_constraint(is_pad * (1 - is_pad))
+        main.add_constraint(is_first * pc[0])                          # pc starts at 0
+        main.add_constraint((1 - is_last) * (pc[1] - pc[0] - 4))       # pc advances by WORD_SIZE
+        for (a, b, c, carry) in lanes:
+            for i in range(4):
+                main.add_constraint((1 - is_pad) * carry[i] * (1 - carry[i]))
+                prev = carry[i - 1] if i else 0
+                main.add_constraint((1 - is_pad) * (a[i] + b[i] + prev - c[i] - carry[i] * 256))
+        for (a, b, c, carry) in lanes:
+            for x in a + b + c:
+                main.add_to_relation(self.range256, 1, [x])
+        main.finalize_logup()
+        table = air.component(8, 1)
+        val = table.get_preprocessed_column("Range256Values")
+        mult = table.next_trace_mask()
+        table.add_to_relation(self.range256, -mult, [val])
+        table.finalize_logup()
+        self.air = air
+        self.main, self.table = main, table
+        self.words = air.serialize()
+
+    # ---- trace filling (host side; trace/coset order, finalized by the backend on upload)
+    def preprocessed_columns(self):
+        n = 1 << self.log_size
+        cols = [None] * self.air.n_columns()[0]
+        is_first = np.zeros(n, np.uint32); is_first[0] = 1
+        is_last = np.zeros(n, np.uint32); is_last[n - 1] = 1
+        cols[self.air.preprocessed_ids["IsFirst"]] = is_first
+        cols[self.air.preprocessed_ids["IsLast"]] = is_last
+        cols[self.air.preprocessed_ids["Range256Values"]] = np.arange(256, dtype=np.uint32)
+        return cols
+
+    def fill_main_trace(self, seed=0, n_padding=0):
+        """ADD chain: every lane adds two pseudo-random 32-bit words per row."""
+        n = 1 << self.log_size
+        rng = np.random.default_rng(seed)
+        cols = []
+        cols.append((4 * np.arange(n, dtype=np.uint64) % P).astype(np.uint32))  # pc
+        pad = np.zeros(n, np.uint32)
+        if n_padding:
+            pad[n - n_padding:] = 1
+        cols.append(pad)
+        hist = np.zeros(256, np.int64)
+        for _ in range(self.n_lanes):
+            a = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+            b = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+            c = (a + b) & 0xFFFFFFFF
+            al = [((a >> (8 * i)) & 0xFF).astype(np.uint32) for i in range(4)]
+            bl = [((b >> (8 * i)) & 0xFF).astype(np.uint32) for i in range(4)]
+            cl = [((c >> (8 * i)) & 0xFF).astype(np.uint32) for i in range(4)]
+            carry, prev = [], np.zeros(n, np.uint32)
+            for i in range(4):
+                s = al[i] + bl[i] + prev
+                prev = (s >> 8).astype(np.uint32)
+                carry.append(prev)
+            cols += al + bl + cl + carry
+            for x in al + bl + cl:
+                hist += np.bincount(x, minlength=256)
+        assert len(cols) == self.air.n_columns()[1] - 1
+        mult = (hist % P).astype(np.uint32)
+        return cols, mult
+
+    def column_log_sizes(self):
+        return self.air.column_log_sizes()
+
+
+def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
+    """The Machine::prove sequence (machine.rs:130-297) over `backend`.  Returns (proof_bytes, claimed_sums, aux)."""
+    config = config or dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)
+    air = machine.air
+    ch = backend.channel()
+    for byte in associated_data:                      # machine.rs:197-200
+        ch.mix_u64(int(byte))
+    log_sizes = [machine.log_size, 8]
+    for ls in log_sizes:                              # machine.rs:204-206
+        ch.mix_u64(ls)
+    prover = backend.prover(machine.words, config)
+    # tree 0: preprocessed (machine.rs:208-228)
+    prover.commit(machine.preprocessed_columns(), ch, coset_order=True)
+    # tree 1: main trace + extension main columns (machine.rs:230-237)
+    prover.commit(list(main_cols) + [mult], ch, coset_order=True)
+    # lookup elements (machine.rs:239-240)
+    params = [(0, 0, 0, 0)] * air.n_params
+    machine.range256.draw(ch, params)
+    # interaction trace per component (machine.rs:242-260); claimed sums mixed before the commit (machine.rs:262-263)
+    inter, claimed = [], []
+    for k, comp in enumerate(air.components):
+        cols, cs = prover.gen_interaction(k, comp.log_size, max(comp.batching) + 1, params)
+        inter.append(cols)
+        claimed.append(cs)
+        inv_n = F.m31_inv((1 << comp.log_size) % P)
+        params[comp.cumsum_shift_param] = F.qm31_mul_m31(cs, inv_n)
+    ch.mix_felts(claimed)
+    prover.commit_interaction(inter, ch)
+    aux = {"channel_at_prove": ch.clone(), "params": params}
+    proof = prover.prove(ch, params)
+    return proof, claimed, aux
+
+
+def verify_claimed_sums(claimed):
+    """machine.rs:343-347: the logup sums of all components must cancel."""
+    tot = (0, 0, 0, 0)
+    for c in claimed:
+        tot = F.qm31_add(tot, c)
+    return tot == (0, 0, 0, 0)

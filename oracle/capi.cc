@@ -186,3 +186,124 @@ void orc_channel_draw_felts(void* c, size_t n, uint32_t* out) {
 void orc_channel_draw_random_bytes(void* c, uint8_t out[32]) { Hash32 h = ((Channel*)c)->draw_random_bytes(); memcpy(out, h.data(), 32); }
 
 }  // extern "C"
+
+// ---- prove / verify -------------------------------------------------------------------------------
+#include "verify.h"
+
+namespace {
+struct OrcProver {
+  Air air;
+  std::vector<Tree> trees;
+  std::vector<std::vector<Col>> trace_evals;  // [tree][col]: the committed evaluations (for logup generation)
+};
+std::string g_err;
+
+struct PostcardReader {
+  const uint8_t* p; size_t n, i = 0;
+  uint64_t varint() { uint64_t v = 0; int s = 0; while (true) { if (i >= n) throw std::runtime_error("postcard: truncated"); uint8_t b = p[i++]; v |= (uint64_t)(b & 0x7f) << s; if (!(b & 0x80)) return v; s += 7; if (s > 63) throw std::runtime_error("postcard: varint too long"); } }
+  M31 m31() { uint64_t v = varint(); if (v >= P) throw std::runtime_error("postcard: M31 out of range"); return M31::raw((uint32_t)v); }
+  QM31 qm31() { M31 a = m31(), b = m31(), c = m31(), d = m31(); return QM31(CM31(a, b), CM31(c, d)); }
+  Hash32 hash() { if (i + 32 > n) throw std::runtime_error("postcard: truncated hash"); Hash32 h; memcpy(h.data(), p + i, 32); i += 32; return h; }
+  MerkleDecommitment decommitment() {
+    MerkleDecommitment d; size_t nh = varint(); for (size_t k = 0; k < nh; ++k) d.hash_witness.push_back(hash());
+    size_t nc = varint(); for (size_t k = 0; k < nc; ++k) d.column_witness.push_back(m31());
+    return d;
+  }
+  FriLayerProof fri_layer() { FriLayerProof l; size_t nw = varint(); for (size_t k = 0; k < nw; ++k) l.fri_witness.push_back(qm31()); l.decommitment = decommitment(); l.commitment = hash(); return l; }
+  Proof proof() {
+    Proof pr;
+    pr.config.pow_bits = (uint32_t)varint(); pr.config.fri.log_blowup_factor = (uint32_t)varint();
+    pr.config.fri.log_last_layer_degree_bound = (uint32_t)varint(); pr.config.fri.n_queries = (uint32_t)varint();
+    size_t nc = varint(); for (size_t k = 0; k < nc; ++k) pr.commitments.push_back(hash());
+    size_t nt = varint(); pr.sampled_values.resize(nt);
+    for (auto& t : pr.sampled_values) { t.resize(varint()); for (auto& c : t) { c.resize(varint()); for (auto& q : c) q = qm31(); } }
+    size_t nd = varint(); for (size_t k = 0; k < nd; ++k) pr.decommitments.push_back(decommitment());
+    size_t nq = varint(); pr.queried_values.resize(nq);
+    for (auto& t : pr.queried_values) { t.resize(varint()); for (auto& v : t) v = m31(); }
+    pr.proof_of_work = varint();
+    pr.fri_proof.first_layer = fri_layer();
+    size_t ni = varint(); for (size_t k = 0; k < ni; ++k) pr.fri_proof.inner_layers.push_back(fri_layer());
+    size_t nl = varint(); for (size_t k = 0; k < nl; ++k) pr.fri_proof.last_layer_poly.push_back(qm31());
+    pr.fri_proof.last_layer_log_size = (uint32_t)varint();
+    if (i != n) throw std::runtime_error("postcard: trailing bytes");
+    return pr;
+  }
+};
+std::vector<QM31> read_params(const uint32_t* p, size_t n) { std::vector<QM31> v(n); for (size_t i = 0; i < n; ++i) v[i] = QM31::from_u32(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]); return v; }
+}  // namespace
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_prover_new(const uint32_t* air_words, size_t n) {
+  try { OrcProver* p = new OrcProver(); p->air = Air::parse(air_words, n); return p; }
+  catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void orc_prover_free(void* p) { delete (OrcProver*)p; }
+
+// TreeBuilder::extend_evals + commit (machine.rs:208-263): interpolate, LDE, Merkle, mix_root
+int orc_prover_commit(void* pp, void* ch, size_t n_cols, const uint32_t* const* cols, const uint32_t* logs, uint32_t log_blowup, uint8_t root[32]) {
+  try {
+    OrcProver* p = (OrcProver*)pp;
+    std::vector<Col> ev(n_cols);
+    for (size_t c = 0; c < n_cols; ++c) { size_t n = (size_t)1 << logs[c]; ev[c].resize(n); for (size_t i = 0; i < n; ++i) ev[c][i] = M31::raw(cols[c][i]); }
+    p->trees.push_back(commit_evals(ev, log_blowup, *(Channel*)ch));
+    p->trace_evals.push_back(std::move(ev));
+    memcpy(root, p->trees.back().merkle.root().data(), 32);
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// generate_interaction_trace for one component (traits.rs:124-145 semantics via LogupTraceGenerator)
+int orc_prover_gen_interaction(void* pp, uint32_t comp, const uint32_t* params, size_t n_params, uint32_t* out_cols, uint32_t claimed[4]) {
+  try {
+    OrcProver* p = (OrcProver*)pp;
+    const Component& c = p->air.comps.at(comp);
+    std::vector<std::vector<Col>> te = p->trace_evals;
+    te.resize(3);
+    auto r = gen_interaction_trace(c, te, read_params(params, n_params));
+    size_t n = (size_t)1 << c.log_size;
+    for (size_t k = 0; k < r.first.size(); ++k) for (size_t i = 0; i < n; ++i) out_cols[k * n + i] = r.first[k][i].v;
+    for (int k = 0; k < 4; ++k) claimed[k] = r.second.coord(k);
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// stwo::prover::prove (machine.rs:286-290) -> postcard bytes of StarkProof
+int orc_prover_prove(void* pp, void* ch, const uint32_t* params, size_t n_params, uint32_t pow_bits, uint32_t log_blowup, uint32_t log_last, uint32_t n_queries,
+                     uint8_t* out, size_t cap, size_t* len) {
+  try {
+    OrcProver* p = (OrcProver*)pp;
+    PcsConfig cfg; cfg.pow_bits = pow_bits; cfg.fri.log_blowup_factor = log_blowup; cfg.fri.log_last_layer_degree_bound = log_last; cfg.fri.n_queries = n_queries;
+    Proof pr = prove(p->air, read_params(params, n_params), p->trees, *(Channel*)ch, cfg);
+    Postcard pc; pc.proof(pr);
+    *len = pc.out.size();
+    if (pc.out.size() > cap) { g_err = "proof buffer too small"; return 2; }
+    memcpy(out, pc.out.data(), pc.out.size());
+    return 0;
+  } catch (ProveError& e) { g_err = e.what(); return 5; }
+  catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// verify postcard proof bytes; `ch` must be in the state the prover's channel had when prove() started
+int orc_verify(const uint32_t* air_words, size_t n_air, const uint32_t* params, size_t n_params, const uint8_t* proof, size_t proof_len,
+               void* ch, const uint32_t* n_cols_per_tree /*3*/, const uint32_t* col_logs_flat) {
+  try {
+    Air air = Air::parse(air_words, n_air);
+    PostcardReader rd{proof, proof_len};
+    Proof pr = rd.proof();
+    // re-encoding must reproduce the bytes (canonical encoding)
+    Postcard pc; pc.proof(pr);
+    if (pc.out.size() != proof_len || memcmp(pc.out.data(), proof, proof_len) != 0) throw VerifyError("postcard: non-canonical encoding");
+    std::vector<std::vector<uint32_t>> logs(3);
+    size_t off = 0;
+    for (int t = 0; t < 3; ++t) { logs[t].assign(col_logs_flat + off, col_logs_flat + off + n_cols_per_tree[t]); off += n_cols_per_tree[t]; }
+    verify(air, read_params(params, n_params), pr, *(Channel*)ch, logs);
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+void* orc_channel_clone(void* c) { return new Channel(*(Channel*)c); }
+
+}  // extern "C"

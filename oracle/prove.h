@@ -10,6 +10,8 @@
 #pragma once
 #include "vcs.h"
 #include <stdexcept>
+#include <memory>
+#include <functional>
 #include <set>
 #include <string>
 

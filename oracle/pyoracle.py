@@ -237,3 +237,83 @@ class Channel:
 
     def draw_random_bytes(self):
         out = (C.c_uint8 * 32)(); lib().orc_channel_draw_random_bytes(self._h, out); return bytes(out)
+
+
+def _clone_channel(ch):
+    c = Channel.__new__(Channel)
+    lib().orc_channel_clone.restype = C.c_void_p
+    c._h = C.c_void_p(lib().orc_channel_clone(ch._h))
+    return c
+
+
+Channel.clone = _clone_channel
+
+
+def last_error():
+    lib().orc_last_error.restype = C.c_char_p
+    return lib().orc_last_error().decode()
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class Prover:
+    """Oracle restatement of CommitmentSchemeProver + stwo::prover::prove over a bytecode AIR."""
+
+    def __init__(self, air_words):
+        self.air_words = np.ascontiguousarray(air_words, dtype=np.uint32)
+        lib().orc_prover_new.restype = C.c_void_p
+        h = lib().orc_prover_new(self.air_words.ctypes.data_as(u32p), C.c_size_t(self.air_words.size))
+        if not h:
+            raise OracleError(last_error())
+        self._h = C.c_void_p(h)
+
+    def __del__(self):
+        try:
+            lib().orc_prover_free(self._h)
+        except Exception:
+            pass
+
+    def commit(self, cols, channel, log_blowup=1):
+        cols, arr, logs = _col_ptrs(cols)
+        root = (C.c_uint8 * 32)()
+        st = lib().orc_prover_commit(self._h, channel._h, C.c_size_t(len(cols)), arr, logs.ctypes.data_as(u32p), C.c_uint32(log_blowup), root)
+        if st:
+            raise OracleError(last_error())
+        return bytes(root)
+
+    def gen_interaction(self, comp, log_size, n_logup_cols, params):
+        params = np.ascontiguousarray(params, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros((4 * n_logup_cols, 1 << log_size), np.uint32)
+        claimed = np.zeros(4, np.uint32)
+        st = lib().orc_prover_gen_interaction(self._h, C.c_uint32(comp), params.ctypes.data_as(u32p), C.c_size_t(params.shape[0]),
+                                              out.ctypes.data_as(u32p), claimed.ctypes.data_as(u32p))
+        if st:
+            raise OracleError(last_error())
+        return out, tuple(int(x) for x in claimed)
+
+    def prove(self, channel, params, pow_bits=5, log_blowup=1, log_last=0, n_queries=3):
+        params = np.ascontiguousarray(params, dtype=np.uint32).reshape(-1, 4)
+        cap = 1 << 26
+        buf = (C.c_uint8 * cap)()
+        ln = C.c_size_t()
+        st = lib().orc_prover_prove(self._h, channel._h, params.ctypes.data_as(u32p), C.c_size_t(params.shape[0]),
+                                    C.c_uint32(pow_bits), C.c_uint32(log_blowup), C.c_uint32(log_last), C.c_uint32(n_queries),
+                                    buf, C.c_size_t(cap), C.byref(ln))
+        if st:
+            raise OracleError(f"prove failed ({st}): {last_error()}")
+        return bytes(buf[:ln.value])
+
+
+def verify(air_words, params, proof_bytes, channel, col_logs):
+    """col_logs: [tree0 logs, tree1 logs, tree2 logs].  Raises OracleError on rejection."""
+    air_words = np.ascontiguousarray(air_words, dtype=np.uint32)
+    params = np.ascontiguousarray(params, dtype=np.uint32).reshape(-1, 4)
+    ncols = np.array([len(x) for x in col_logs], dtype=np.uint32)
+    flat = np.array([l for t in col_logs for l in t], dtype=np.uint32)
+    buf = (C.c_uint8 * len(proof_bytes)).from_buffer_copy(proof_bytes)
+    st = lib().orc_verify(air_words.ctypes.data_as(u32p), C.c_size_t(air_words.size), params.ctypes.data_as(u32p), C.c_size_t(params.shape[0]),
+                          buf, C.c_size_t(len(proof_bytes)), channel._h, ncols.ctypes.data_as(u32p), flat.ctypes.data_as(u32p))
+    if st:
+        raise OracleError(last_error())
