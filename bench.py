@@ -298,11 +298,14 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import pyoracle as orc
-        sample = min(args.cpu_sample_cols, total_cols)
-        tcpu = cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample)
-        cpu_baseline = {"value": n_rows / (tcpu * total_cols / sample), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                        "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle, {tcpu:.1f} s), scaled linearly in columns"}
+        try:
+            from oracle import pyoracle as orc
+            sample = min(args.cpu_sample_cols, total_cols)
+            tcpu = cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample)
+            cpu_baseline = {"value": n_rows / (tcpu * total_cols / sample), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                            "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle, {tcpu:.1f} s), scaled linearly in columns"}
+        except Exception as e:  # the GPU numbers must still be reported
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
