@@ -114,6 +114,50 @@ nb200_status nb200_commit_evals(nb200_ctx*, const nb200_cols* const* eval_batche
                                 nb200_cols** coeffs_io /* n_batches */, nb200_cols** lde_io /* n_batches */,
                                 nb200_tree** tree_out, uint8_t root[32]);
 
+/* ---- Blake2sChannel (stwo core/channel/blake2s.rs; used at machine.rs:197-206,240,262) --------------- */
+/* The Fiat-Shamir transcript is sequential host work; it is part of the library so that the Rust shim and the
+ * coarse nb200_prove share one implementation.  ctx may be NULL (defaults for the flavour switches). */
+typedef struct nb200_channel nb200_channel;
+nb200_status nb200_channel_new(nb200_ctx*, nb200_channel** out);
+nb200_status nb200_channel_clone(const nb200_channel*, nb200_channel** out);
+void nb200_channel_free(nb200_channel*);
+void nb200_channel_digest(const nb200_channel*, uint8_t out[32]);
+void nb200_channel_mix_u64(nb200_channel*, uint64_t v);
+void nb200_channel_mix_u32s(nb200_channel*, const uint32_t* words, size_t n);
+void nb200_channel_mix_felts(nb200_channel*, const uint32_t* qm31s, size_t n);
+void nb200_channel_mix_root(nb200_channel*, const uint8_t root[32]); /* Blake2sMerkleChannel::mix_root */
+void nb200_channel_draw_felt(nb200_channel*, uint32_t out[4]);
+void nb200_channel_draw_felts(nb200_channel*, size_t n, uint32_t* out);
+void nb200_channel_draw_random_bytes(nb200_channel*, uint8_t out[32]);
+
+/* ---- AIR: FrameworkComponent<E> as data (SSA bytecode recorded from `add_constraints`, traits.rs:45-50) ---- */
+typedef struct nb200_air nb200_air;
+nb200_status nb200_air_load(nb200_ctx*, const uint32_t* words, size_t n_words, nb200_air** out);
+void nb200_air_free(nb200_air*);
+uint32_t nb200_air_n_params(const nb200_air*);
+uint32_t nb200_air_n_components(const nb200_air*);
+
+/* ---- CommitmentSchemeProver<B, Blake2sMerkleChannel> (machine.rs:202-203) ------------------------------ */
+typedef struct nb200_scheme nb200_scheme;
+/* PcsConfig { pow_bits, FriConfig { log_blowup_factor, log_last_layer_degree_bound, n_queries } } (machine.rs:184) */
+nb200_status nb200_scheme_new(nb200_ctx*, uint32_t pow_bits, uint32_t log_blowup, uint32_t log_last_layer_degree_bound,
+                              uint32_t n_queries, nb200_scheme** out);
+void nb200_scheme_free(nb200_scheme*);
+/* tree_builder.extend_evals(batches...); tree_builder.commit(channel)  (machine.rs:208-263): interpolate, LDE,
+ * Merkle, mix_root.  The evaluation batches are only read. */
+nb200_status nb200_scheme_commit(nb200_scheme*, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel*, uint8_t root[32]);
+/* generate_interaction_trace for one component (machine.rs:242-260; LogupTraceGenerator semantics) from the committed
+ * preprocessed (tree0) and main (tree1) evaluation batches; params = n_params QM31 (lookup elements).
+ * Out: a new batch of 4 * n_logup_columns columns and the component's claimed sum.  SURVEY §8 row f2. */
+nb200_status nb200_gen_interaction_trace(nb200_ctx*, const nb200_air*, uint32_t component,
+                                         const nb200_cols* const* tree0, size_t n0, const nb200_cols* const* tree1, size_t n1,
+                                         const uint32_t* params, size_t n_params, nb200_cols** out, uint32_t claimed_sum[4]);
+/* stwo::prover::prove::<B, Blake2sMerkleChannel>(components, channel, commitment_scheme)  (machine.rs:286-290).
+ * Requires the three trace trees to be committed.  Output: postcard(StarkProof) bytes, malloc'ed (nb200_free).
+ * Returns NB200_ERR_CONSTRAINTS for ProvingError::ConstraintsNotSatisfied. */
+nb200_status nb200_prove(nb200_scheme*, const nb200_air*, const uint32_t* params, size_t n_params, nb200_channel*,
+                         uint8_t** proof_out, size_t* proof_len);
+
 #ifdef __cplusplus
 }
 #endif

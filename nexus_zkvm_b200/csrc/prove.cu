@@ -1,0 +1,663 @@
+// Proving orchestrator: CommitmentSchemeProver / TreeBuilder and stwo::prover::prove + prove_values, FRI prover,
+// proof assembly and postcard serialisation — the host logic that sequences the CUDA kernels between Fiat-Shamir
+// round trips.  Replaces everything the reference reaches through
+//   CommitmentSchemeProver::<SimdBackend, Blake2sMerkleChannel>::new / tree_builder / commit   prover/src/machine.rs:202-263
+//   stwo::prover::prove::<SimdBackend, Blake2sMerkleChannel>(components, channel, scheme)         prover/src/machine.rs:286-290
+// (stwo @0790eba prover/mod.rs, prover/pcs/mod.rs, prover/fri.rs, prover/air/accumulation.rs, core/proof.rs).
+// The transcript (channel) is host-side by nature; every data-parallel step is a kernel launch on ctx->stream.
+#include "pcs.h"
+#include "host_channel.h"
+#include "circle_host.h"
+#include <algorithm>
+#include <map>
+#include <set>
+#include <memory>
+#include <cstring>
+
+struct nb200_channel { nb::HostChannel ch; };
+struct nb200_air { nb::AirProgram prog; };
+
+namespace nb {
+
+struct SchemeTree {
+  std::vector<nb200_cols*> coeffs, ldes;  // owned batches, commitment order
+  struct ColLoc { u32 batch, idx, log; };
+  std::vector<ColLoc> cols;               // global column index -> (batch, index in batch, polynomial log size)
+  nb200_tree* merkle = nullptr;
+  const u32* coeff_ptr(size_t g) const { return coeffs[cols[g].batch]->col(cols[g].idx); }
+  const u32* lde_ptr(size_t g) const { return ldes[cols[g].batch]->col(cols[g].idx); }
+};
+
+}  // namespace nb
+
+struct nb200_scheme {
+  nb200_ctx* ctx = nullptr;
+  uint32_t pow_bits = 5, log_blowup = 1, log_last = 0, n_queries = 3;  // PcsConfig::default() [risk A.4]
+  std::vector<nb::SchemeTree> trees;
+};
+
+extern "C" nb200_status nb200_cols_alloc(nb200_ctx*, size_t, uint32_t, nb200_cols**);
+extern "C" void nb200_cols_free(nb200_ctx*, nb200_cols*);
+extern "C" void nb200_tree_free(nb200_ctx*, nb200_tree*);
+
+namespace nb {
+
+// RAII for temporary batches / trees
+struct ColsGuard {
+  nb200_ctx* ctx; nb200_cols* c = nullptr;
+  explicit ColsGuard(nb200_ctx* x) : ctx(x) {}
+  ~ColsGuard() { if (c) nb200_cols_free(ctx, c); }
+  nb200_cols* release() { nb200_cols* r = c; c = nullptr; return r; }
+};
+
+static void free_tree(nb200_ctx* ctx, SchemeTree& t) {
+  for (auto* c : t.coeffs) nb200_cols_free(ctx, c);
+  for (auto* c : t.ldes) nb200_cols_free(ctx, c);
+  if (t.merkle) nb200_tree_free(ctx, t.merkle);
+  t = SchemeTree();
+}
+
+static nb200_status finish_tree(nb200_ctx* ctx, SchemeTree& t, HostChannel& ch) {
+  std::vector<ColRef> refs;
+  t.cols.clear();
+  for (size_t b = 0; b < t.ldes.size(); ++b)
+    for (size_t c = 0; c < t.ldes[b]->n_cols; ++c) {
+      refs.push_back(ColRef{t.ldes[b]->col(c), t.ldes[b]->log_size});
+      t.cols.push_back(SchemeTree::ColLoc{(u32)b, (u32)c, t.coeffs[b]->log_size});
+    }
+  NB_TRY(merkle_commit(ctx, refs, &t.merkle));
+  ch.mix_root(t.merkle->root);
+  return NB200_OK;
+}
+
+// TreeBuilder::extend_evals + commit
+nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals, size_t n, HostChannel& ch, uint8_t root[32]) {
+  nb200_ctx* ctx = s->ctx;
+  u32 max_log = 0;
+  for (size_t b = 0; b < n; ++b) max_log = std::max(max_log, evals[b]->log_size + s->log_blowup);
+  if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
+  SchemeTree t;
+  for (size_t b = 0; b < n; ++b) {
+    nb200_cols *co = nullptr, *lde = nullptr;
+    NB_TRY(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size, &co));
+    t.coeffs.push_back(co);
+    NB_TRY(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size + s->log_blowup, &lde));
+    t.ldes.push_back(lde);
+    NB_TRY(fft_interpolate(ctx, evals[b]->d, co->d, co->n_cols, co->log_size));
+    NB_TRY(fft_evaluate(ctx, co->d, co->log_size, lde->d, lde->log_size, co->n_cols));
+  }
+  nb200_status st = finish_tree(ctx, t, ch);
+  if (st != NB200_OK) { free_tree(ctx, t); return st; }
+  if (root) memcpy(root, t.merkle->root, 32);
+  s->trees.push_back(std::move(t));
+  return NB200_OK;
+}
+
+// ---- host-side point-mode interpreter (PointEvaluator) for the prover's sanity check ----
+static qm31 from_partial_evals(const qm31 v[4]) {
+  qm31 I = qm31_make(0, 1, 0, 0), U = qm31_make(0, 0, 1, 0), IU = qm31_make(0, 0, 0, 1);
+  return qm31_add(qm31_add(v[0], qm31_mul(v[1], I)), qm31_add(qm31_mul(v[2], U), qm31_mul(v[3], IU)));
+}
+template <class OnC>
+static void run_point(const std::vector<AirInstr>& prog, const qm31* mask, const std::vector<qm31>& params, std::vector<qm31>& br, std::vector<qm31>& er, OnC on_c) {
+  for (const AirInstr& in : prog) {
+    switch (in.op) {
+      case OP_LOADM: br[in.dst] = mask[in.a]; break;
+      case OP_CONSTB: br[in.dst] = qm31_from_m31(in.a); break;
+      case OP_ADDB: br[in.dst] = qm31_add(br[in.a], br[in.b]); break;
+      case OP_SUBB: br[in.dst] = qm31_sub(br[in.a], br[in.b]); break;
+      case OP_MULB: br[in.dst] = qm31_mul(br[in.a], br[in.b]); break;
+      case OP_NEGB: br[in.dst] = qm31_neg(br[in.a]); break;
+      case OP_PARAME: er[in.dst] = params[in.a]; break;
+      case OP_ADDE: er[in.dst] = qm31_add(er[in.a], er[in.b]); break;
+      case OP_SUBE: er[in.dst] = qm31_sub(er[in.a], er[in.b]); break;
+      case OP_MULE: er[in.dst] = qm31_mul(er[in.a], er[in.b]); break;
+      case OP_NEGE: er[in.dst] = qm31_neg(er[in.a]); break;
+      case OP_ADDEB: er[in.dst] = qm31_add(er[in.a], br[in.b]); break;
+      case OP_SUBEB: er[in.dst] = qm31_sub(er[in.a], br[in.b]); break;
+      case OP_MULEB: er[in.dst] = qm31_mul(er[in.a], br[in.b]); break;
+      case OP_BTOE: er[in.dst] = br[in.a]; break;
+      case OP_LOADME: er[in.dst] = from_partial_evals(mask + in.a); break;
+      case OP_CONSTRB: on_c(br[in.a]); break;
+      case OP_CONSTRE: on_c(er[in.a]); break;
+      default: break;
+    }
+  }
+}
+// coset_vanishing of CanonicCoset(log).coset at a QM31 point
+static qm31 coset_vanishing_q(u32 log_size, qpoint p) {
+  HCoset c = HCoset::odds(log_size);
+  u32 shift = idx_add(idx_neg(c.initial_index), c.step_index >> 1);
+  qpoint r = qp_add(p, qp_from_m31(index_to_point(shift)));
+  qm31 x = r.x;
+  for (u32 i = 1; i < log_size; ++i) x = qm31_double_x(x);
+  return x;
+}
+
+// ---- postcard (serde) writer for StarkProof ----                                              [risk A.12]
+struct Postcard {
+  std::vector<uint8_t> out;
+  void varint(uint64_t v) { while (v >= 0x80) { out.push_back((uint8_t)(v | 0x80)); v >>= 7; } out.push_back((uint8_t)v); }
+  void q(const qm31& v) { for (int k = 0; k < 4; ++k) varint(v.c[k]); }
+  void hash(const uint8_t* h) { out.insert(out.end(), h, h + 32); }
+};
+struct Decommitment { std::vector<uint8_t> hash_witness; std::vector<u32> column_witness; };
+struct FriLayerProof { std::vector<qm31> fri_witness; Decommitment decommitment; uint8_t commitment[32]; };
+static void put_decommitment(Postcard& pc, const Decommitment& d) {
+  pc.varint(d.hash_witness.size() / 32); pc.out.insert(pc.out.end(), d.hash_witness.begin(), d.hash_witness.end());
+  pc.varint(d.column_witness.size()); for (u32 v : d.column_witness) pc.varint(v);
+}
+static void put_fri_layer(Postcard& pc, const FriLayerProof& l) {
+  pc.varint(l.fri_witness.size()); for (auto& v : l.fri_witness) pc.q(v);
+  put_decommitment(pc, l.decommitment); pc.hash(l.commitment);
+}
+
+// ---- queries (core/queries.rs) ----
+struct Queries {
+  std::vector<u64> positions; u32 log_domain_size = 0;
+  static Queries generate(HostChannel& ch, u32 log_domain_size, size_t n_queries) {
+    std::set<u64> q; size_t cnt = 0; u64 mask = ((u64)1 << log_domain_size) - 1;
+    while (true) {
+      uint8_t r[32]; ch.draw_random_bytes(r);
+      for (int k = 0; k < 8; ++k) {
+        u32 w = (u32)r[4 * k] | ((u32)r[4 * k + 1] << 8) | ((u32)r[4 * k + 2] << 16) | ((u32)r[4 * k + 3] << 24);
+        q.insert((u64)w & mask);
+        if (++cnt == n_queries) { Queries o; o.positions.assign(q.begin(), q.end()); o.log_domain_size = log_domain_size; return o; }
+      }
+    }
+  }
+  Queries fold(u32 n) const {
+    Queries o; o.log_domain_size = log_domain_size - n;
+    for (u64 p : positions) { u64 f = p >> n; if (o.positions.empty() || o.positions.back() != f) o.positions.push_back(f); }
+    return o;
+  }
+};
+
+// decommitment positions + witness evaluations of one FRI layer column (compute_decommitment_positions_and_witness_evals)
+static nb200_status positions_and_witness(nb200_ctx* ctx, const nb200_cols* col4, const std::vector<u64>& queries, std::vector<u64>& positions, std::vector<qm31>& witness) {
+  std::vector<u64> need;
+  size_t i = 0;
+  while (i < queries.size()) {
+    size_t j = i; u64 key = queries[i] >> 1;
+    while (j < queries.size() && (queries[j] >> 1) == key) ++j;
+    size_t qi = i;
+    for (u64 pos = key << 1; pos < (key << 1) + 2; ++pos) {
+      positions.push_back(pos);
+      if (qi < j && queries[qi] == pos) { ++qi; continue; }
+      need.push_back(pos);
+    }
+    i = j;
+  }
+  std::vector<const u32*> addrs;
+  for (u64 p : need) for (int k = 0; k < 4; ++k) addrs.push_back(col4->col(k) + p);
+  std::vector<u32> vals(addrs.size());
+  NB_TRY(gather_u32(ctx, addrs, vals.data()));
+  for (size_t w = 0; w < need.size(); ++w) witness.push_back(qm31_make(vals[4 * w], vals[4 * w + 1], vals[4 * w + 2], vals[4 * w + 3]));
+  return NB200_OK;
+}
+
+static qm31 load_param(const u32* p) { return qm31_make(p[0], p[1], p[2], p[3]); }
+
+// stwo::prover::prove
+nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vector<qm31>& params, HostChannel& ch, std::vector<uint8_t>& proof_bytes) {
+  nb200_ctx* ctx = s->ctx;
+  NB_ARG(ctx, s->trees.size() == 3, "prove: the preprocessed, main and interaction trees must be committed first");
+  NB_ARG(ctx, params.size() == air.n_params, "prove: parameter table size");
+  const u32 blow = s->log_blowup;
+
+  // ---------------- composition polynomial ----------------
+  qm31 random_coeff = ch.draw_felt();
+  size_t n_total = 0; u32 comp_log = 0;
+  for (auto& c : air.comps) { n_total += c.n_constraints; comp_log = std::max(comp_log, c.eval_log()); }
+  NB_TRY(twiddles_prepare(ctx, comp_log + blow));
+  std::vector<qm31> powers(n_total);
+  { qm31 a = qm31_one(); for (size_t i = 0; i < n_total; ++i) { powers[i] = a; a = qm31_mul(a, random_coeff); } }
+  u32* d_params = nullptr;
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(params.size(), 1) * 16));
+  if (!params.empty()) NB_CUDA(ctx, cudaMemcpyAsync(d_params, params.data(), params.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+
+  std::map<u32, nb200_cols*> acc;  // eval_log -> 4-column accumulator
+  auto free_acc = [&]() { for (auto& kv : acc) nb200_cols_free(ctx, kv.second); acc.clear(); };
+  size_t g0 = 0;
+  for (const AirComponent& c : air.comps) {
+    const u32 elog = c.eval_log();
+    // evaluate every batch this component reads on its evaluation domain
+    std::map<std::pair<u32, u32>, nb200_cols*> ext;
+    auto free_ext = [&]() { for (auto& kv : ext) nb200_cols_free(ctx, kv.second); ext.clear(); };
+    std::vector<const u32*> mask_cols(c.masks.size());
+    nb200_status st = NB200_OK;
+    for (size_t m = 0; m < c.masks.size() && st == NB200_OK; ++m) {
+      const AirMask& mk = c.masks[m];
+      if (mk.col >= s->trees[mk.tree].cols.size()) { st = set_err(ctx, NB200_ERR_ARG, "prove: AIR references a column that was not committed"); break; }
+      const SchemeTree::ColLoc& loc = s->trees[mk.tree].cols[mk.col];
+      if (loc.log != c.log_size) { st = set_err(ctx, NB200_ERR_ARG, "prove: column size differs from its component's log_size"); break; }
+      auto key = std::make_pair(mk.tree, loc.batch);
+      if (!ext.count(key)) {
+        const nb200_cols* co = s->trees[mk.tree].coeffs[loc.batch];
+        nb200_cols* e = nullptr;
+        st = nb200_cols_alloc(ctx, co->n_cols, elog, &e);
+        if (st != NB200_OK) break;
+        ext[key] = e;
+        st = fft_evaluate(ctx, co->d, co->log_size, e->d, elog, co->n_cols);
+      }
+      if (st == NB200_OK) mask_cols[m] = ext[key]->col(loc.idx);
+    }
+    if (st == NB200_OK && !acc.count(elog)) {
+      nb200_cols* a = nullptr;
+      st = nb200_cols_alloc(ctx, 4, elog, &a);
+      if (st == NB200_OK) { acc[elog] = a; if (cudaMemsetAsync(a->d, 0, ((size_t)16) << elog, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "memset"); }
+    }
+    if (st == NB200_OK) {
+      std::vector<qm31> coeff(c.n_constraints);
+      for (u32 k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
+      u32* accp[4] = {acc[elog]->col(0), acc[elog]->col(1), acc[elog]->col(2), acc[elog]->col(3)};
+      st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp);
+    }
+    g0 += c.n_constraints;
+    free_ext();
+    if (st != NB200_OK) { free_acc(); dfree(ctx, d_params); return st; }
+  }
+  // DomainEvaluationAccumulator::finalize: fold the per-size accumulators upwards
+  nb200_cols* cur = nullptr;  // coefficients of the running composition (4 columns)
+  for (auto& kv : acc) {
+    nb200_cols* a = kv.second;
+    if (cur) {
+      ColsGuard tmp(ctx);
+      NB_TRY(nb200_cols_alloc(ctx, 4, kv.first, &tmp.c));
+      NB_TRY(fft_evaluate(ctx, cur->d, cur->log_size, tmp.c->d, kv.first, 4));
+      NB_TRY(add_inplace(ctx, a->d, tmp.c->d, (size_t)4 << kv.first));
+      nb200_cols_free(ctx, cur);
+    }
+    NB_TRY(fft_interpolate(ctx, a->d, a->d, 4, kv.first));
+    cur = a; kv.second = nullptr;
+  }
+  acc.clear();
+  NB_ARG(ctx, cur != nullptr && cur->log_size == comp_log, "prove: no constraints");
+  // tree 3: the composition's 4 coordinate polynomials
+  {
+    SchemeTree t;
+    t.coeffs.push_back(cur);
+    nb200_cols* lde = nullptr;
+    NB_TRY(nb200_cols_alloc(ctx, 4, comp_log + blow, &lde));
+    t.ldes.push_back(lde);
+    NB_TRY(fft_evaluate(ctx, cur->d, comp_log, lde->d, comp_log + blow, 4));
+    NB_TRY(finish_tree(ctx, t, ch));
+    s->trees.push_back(std::move(t));
+  }
+
+  // ---------------- OODS sampling ----------------
+  qpoint oods;
+  {
+    qm31 t = ch.draw_felt();
+    qm31 t2 = qm31_sqr(t);
+    qm31 ip = qm31_inv(qm31_add(t2, qm31_one()));
+    oods.x = qm31_mul(qm31_sub(qm31_one(), t2), ip);
+    oods.y = qm31_mul(qm31_add(t, t), ip);
+  }
+  // per tree / column: offsets in declaration order (Components::mask_points)
+  std::vector<std::vector<std::vector<int32_t>>> offs(4);
+  for (int t = 0; t < 4; ++t) offs[t].resize(s->trees[t].cols.size());
+  for (const AirComponent& c : air.comps)
+    for (const AirMask& m : c.masks) {
+      auto& o = offs[m.tree][m.col];
+      if (std::find(o.begin(), o.end(), m.off) == o.end()) o.push_back(m.off);
+    }
+  for (auto& o : offs[3]) o.assign(1, 0);
+  auto mask_point = [&](u32 log_size, int32_t off) -> qpoint {
+    if (off == 0) return oods;
+    u32 step = canonic_step_index(log_size);
+    u32 idx = idx_mul(step, (u64)(off < 0 ? -off : off));
+    if (off < 0) idx = idx_neg(idx);
+    return qp_add(oods, qp_from_m31(index_to_point(idx)));
+  };
+  std::vector<std::vector<std::vector<qpoint>>> points(4);
+  std::vector<std::vector<std::vector<qm31>>> sampled(4);
+  for (int t = 0; t < 4; ++t) {
+    const SchemeTree& tr = s->trees[t];
+    points[t].resize(tr.cols.size()); sampled[t].resize(tr.cols.size());
+    for (size_t g = 0; g < tr.cols.size(); ++g)
+      for (int32_t o : offs[t][g]) points[t][g].push_back(mask_point(tr.cols[g].log, o));
+    // groups of consecutive columns of one batch with the same offsets -> one eval_at_points launch
+    size_t g = 0;
+    while (g < tr.cols.size()) {
+      size_t h = g + 1;
+      while (h < tr.cols.size() && tr.cols[h].batch == tr.cols[g].batch && offs[t][h] == offs[t][g]) ++h;
+      size_t np = offs[t][g].size();
+      if (np > 0) {
+        std::vector<u32> pts(np * 8);
+        for (size_t k = 0; k < np; ++k) { memcpy(&pts[8 * k], points[t][g][k].x.c, 16); memcpy(&pts[8 * k + 4], points[t][g][k].y.c, 16); }
+        std::vector<u32> out((h - g) * np * 4);
+        NB_TRY(eval_at_points(ctx, tr.coeff_ptr(g), h - g, tr.cols[g].log, pts.data(), np, out.data()));
+        for (size_t c = g; c < h; ++c) for (size_t k = 0; k < np; ++k) sampled[t][c].push_back(load_param(&out[((c - g) * np + k) * 4]));
+      }
+      g = h;
+    }
+  }
+  {
+    std::vector<qm31> flat;
+    for (auto& t : sampled) for (auto& c : t) for (auto& v : c) flat.push_back(v);
+    ch.mix_felts(flat.data(), flat.size());
+  }
+
+  // ---------------- DEEP quotients ----------------
+  qm31 q_coeff = ch.draw_felt();
+  struct CRef { int t; size_t g; u32 log; };
+  std::vector<CRef> all;
+  for (int t = 0; t < 4; ++t) for (size_t g = 0; g < s->trees[t].cols.size(); ++g) all.push_back(CRef{t, g, s->trees[t].cols[g].log + blow});
+  std::stable_sort(all.begin(), all.end(), [](const CRef& a, const CRef& b) { return a.log > b.log; });
+  std::vector<nb200_cols*> quotients; std::vector<u32> qlogs;
+  auto free_q = [&]() { for (auto* q : quotients) nb200_cols_free(ctx, q); quotients.clear(); };
+  for (size_t i = 0; i < all.size();) {
+    size_t j = i; while (j < all.size() && all[j].log == all[i].log) ++j;
+    const u32 lg = all[i].log;
+    // ColumnSampleBatch::new_vec: group samples by point, first-seen order                   [risk: IndexMap vs BTreeMap]
+    struct HB { qpoint p; std::vector<std::pair<size_t, qm31>> cols; };
+    std::vector<HB> hb;
+    for (size_t k = i; k < j; ++k) {
+      const CRef& r = all[k];
+      for (size_t pi = 0; pi < points[r.t][r.g].size(); ++pi) {
+        const qpoint& p = points[r.t][r.g][pi];
+        size_t b = 0;
+        for (; b < hb.size(); ++b) if (qm31_eq(hb[b].p.x, p.x) && qm31_eq(hb[b].p.y, p.y)) break;
+        if (b == hb.size()) hb.push_back(HB{p, {}});
+        hb[b].cols.push_back({k, sampled[r.t][r.g][pi]});
+      }
+    }
+    std::vector<QBatchDev> qb(hb.size()); std::vector<QEntryDev> qe;
+    for (size_t b = 0; b < hb.size(); ++b) {
+      QBatchDev& B = qb[b];
+      const qpoint& p = hb[b].p;
+      B.prx[0] = p.x.c[0]; B.prx[1] = p.x.c[1]; B.pix[0] = p.x.c[2]; B.pix[1] = p.x.c[3];
+      B.pry[0] = p.y.c[0]; B.pry[1] = p.y.c[1]; B.piy[0] = p.y.c[2]; B.piy[1] = p.y.c[3];
+      qm31 alpha = qm31_one(), sa = qm31_zero(), sb = qm31_zero();
+      B.first = (u32)qe.size(); B.count = (u32)hb[b].cols.size();
+      for (auto& cv : hb[b].cols) {
+        alpha = qm31_mul(alpha, q_coeff);
+        // complex_conjugate_line_coeffs
+        qm31 a = qm31_sub(qm31_conj(cv.second), cv.second);
+        qm31 c = qm31_sub(qm31_conj(p.y), p.y);
+        qm31 bq = qm31_sub(qm31_mul(cv.second, c), qm31_mul(a, p.y));
+        sa = qm31_add(sa, qm31_mul(alpha, a)); sb = qm31_add(sb, qm31_mul(alpha, bq));
+        qm31 ac = qm31_mul(alpha, c);
+        QEntryDev e; e.col = s->trees[all[cv.first].t].lde_ptr(all[cv.first].g); memcpy(e.c, ac.c, 16); e.pad[0] = e.pad[1] = 0;
+        qe.push_back(e);
+      }
+      memcpy(B.A, sa.c, 16); memcpy(B.B, sb.c, 16);
+      qm31 bc = qm31_pow(q_coeff, hb[b].cols.size());
+      memcpy(B.coeff, bc.c, 16);
+    }
+    ColsGuard dom(ctx);
+    nb200_status st = nb200_cols_alloc(ctx, 2, lg, &dom.c);
+    if (st == NB200_OK) st = domain_points(ctx, lg, dom.c->col(0), dom.c->col(1));
+    nb200_cols* q = nullptr;
+    if (st == NB200_OK) st = nb200_cols_alloc(ctx, 4, lg, &q);
+    if (st == NB200_OK) { quotients.push_back(q); qlogs.push_back(lg); st = quotients_launch(ctx, qb.data(), qb.size(), qe.data(), qe.size(), dom.c->col(0), dom.c->col(1), lg, q->d); }
+    if (st != NB200_OK) { free_q(); dfree(ctx, d_params); return st; }
+    i = j;
+  }
+
+  // ---------------- FRI commit phase ----------------
+  struct Layer { nb200_cols* cols; nb200_tree* tree; u32 log; };
+  std::vector<Layer> inner;
+  nb200_tree* first_tree = nullptr;
+  auto cleanup_fri = [&]() { for (auto& l : inner) { if (l.cols) nb200_cols_free(ctx, l.cols); if (l.tree) nb200_tree_free(ctx, l.tree); } inner.clear(); if (first_tree) nb200_tree_free(ctx, first_tree); first_tree = nullptr; free_q(); dfree(ctx, d_params); };
+#define NB_TRYF(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) { cleanup_fri(); return _s; } } while (0)
+  {
+    std::vector<ColRef> refs;
+    for (size_t g = 0; g < quotients.size(); ++g) for (int k = 0; k < 4; ++k) refs.push_back(ColRef{quotients[g]->col(k), qlogs[g]});
+    NB_TRYF(merkle_commit(ctx, refs, &first_tree));
+    ch.mix_root(first_tree->root);
+  }
+  qm31 circle_alpha = ch.draw_felt();
+  const size_t last_domain = (size_t)1 << (s->log_last + blow);
+  u32 L = qlogs[0] - 1;
+  nb200_cols* layer = nullptr;
+  NB_TRYF(nb200_cols_alloc(ctx, 4, L, &layer));
+  if (cudaMemsetAsync(layer->d, 0, (size_t)16 << L, ctx->stream) != cudaSuccess) { nb200_cols_free(ctx, layer); cleanup_fri(); return set_err(ctx, NB200_ERR_CUDA, "memset"); }
+  size_t ci = 0;
+  std::vector<qm31> last_layer_poly;
+  while (((size_t)1 << L) > last_domain) {
+    while (ci < quotients.size() && qlogs[ci] - 1 == L) {
+      nb200_status st = fold_circle_into_line(ctx, layer->d, quotients[ci]->d, qlogs[ci], circle_alpha);
+      if (st != NB200_OK) { nb200_cols_free(ctx, layer); cleanup_fri(); return st; }
+      ++ci;
+    }
+    Layer ly{layer, nullptr, L};
+    inner.push_back(ly);
+    std::vector<ColRef> refs; for (int k = 0; k < 4; ++k) refs.push_back(ColRef{layer->col(k), L});
+    NB_TRYF(merkle_commit(ctx, refs, &inner.back().tree));
+    ch.mix_root(inner.back().tree->root);
+    qm31 alpha = ch.draw_felt();
+    nb200_cols* next = nullptr;
+    NB_TRYF(nb200_cols_alloc(ctx, 4, L - 1, &next));
+    nb200_status st = fold_line(ctx, next->d, layer->d, L, alpha);
+    if (st != NB200_OK) { nb200_cols_free(ctx, next); cleanup_fri(); return st; }
+    layer = next; L -= 1;
+  }
+  {
+    // circle columns that fold exactly into the last layer's size would be an upstream assertion failure
+    nb200_status st = NB200_OK;
+    if (ci != quotients.size()) st = set_err(ctx, NB200_ERR_STATE, "fri: not all columns consumed");
+    if (st == NB200_OK && ((size_t)1 << L) != last_domain) st = set_err(ctx, NB200_ERR_STATE, "fri: last layer size");
+    std::vector<u32> host((size_t)4 << L);
+    if (st == NB200_OK && cudaMemcpyAsync(host.data(), layer->d, host.size() * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "d2h");
+    if (st == NB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "sync");
+    nb200_cols_free(ctx, layer); layer = nullptr;
+    if (st != NB200_OK) { cleanup_fri(); return st; }
+    // LineEvaluation::interpolate on the host (the last layer has 2^(log_last + blowup) points)
+    size_t n = (size_t)1 << L;
+    std::vector<qm31> v(n);
+    for (size_t i2 = 0; i2 < n; ++i2) v[bit_reverse_u32((u32)i2, L)] = qm31_make(host[i2], host[n + i2], host[2 * n + i2], host[3 * n + i2]);
+    HLineDomain d = HLineDomain::make(HCoset::half_odds(L));
+    while (d.size() > 1) {
+      size_t ds = d.size();
+      for (size_t c0 = 0; c0 < n; c0 += ds)
+        for (size_t i2 = 0; i2 < ds / 2; ++i2) {
+          u32 xi = m31_inv(d.at(i2));
+          qm31 a = v[c0 + i2], b = v[c0 + ds / 2 + i2];
+          v[c0 + i2] = qm31_add(a, b);
+          v[c0 + ds / 2 + i2] = qm31_mul_m31(qm31_sub(a, b), xi);
+        }
+      d = d.dbl();
+    }
+    u32 sc = m31_inv((u32)(n % P31));
+    for (auto& qv : v) qv = qm31_mul_m31(qv, sc);
+    // v is the LinePoly storage order (bit-reversed); ordered coefficients = bit-reversed again
+    std::vector<qm31> ordered(n);
+    for (size_t i2 = 0; i2 < n; ++i2) ordered[bit_reverse_u32((u32)i2, L)] = v[i2];
+    size_t bound = (size_t)1 << s->log_last;
+    for (size_t i2 = bound; i2 < n; ++i2) if (!qm31_is_zero(ordered[i2])) { cleanup_fri(); return set_err(ctx, NB200_ERR_CONSTRAINTS, "fri: last layer has invalid degree (constraints not satisfied)"); }
+    last_layer_poly.resize(bound);
+    for (size_t i2 = 0; i2 < bound; ++i2) last_layer_poly[bit_reverse_u32((u32)i2, s->log_last)] = ordered[i2];
+    ch.mix_felts(last_layer_poly.data(), last_layer_poly.size());
+  }
+
+  // ---------------- proof of work, queries, decommitments ----------------
+  uint64_t nonce = 0;
+  NB_TRYF(grind(ctx, ch.digest.data(), s->pow_bits, &nonce));
+  ch.mix_u64(nonce);
+  const u32 max_log = qlogs[0];
+  Queries queries = Queries::generate(ch, max_log, s->n_queries);
+  std::vector<std::pair<u32, std::vector<u64>>> by_log;
+  for (u32 lg : qlogs) by_log.push_back({lg, queries.fold(max_log - lg).positions});
+
+  FriLayerProof first_proof; std::vector<FriLayerProof> inner_proofs(inner.size());
+  {
+    std::vector<std::pair<u32, std::vector<u64>>> dpos;
+    for (size_t g = 0; g < quotients.size(); ++g) {
+      std::vector<u64> pos;
+      NB_TRYF(positions_and_witness(ctx, quotients[g], queries.fold(max_log - qlogs[g]).positions, pos, first_proof.fri_witness));
+      dpos.push_back({qlogs[g], pos});
+    }
+    std::vector<ColRef> refs;
+    for (size_t g = 0; g < quotients.size(); ++g) for (int k = 0; k < 4; ++k) refs.push_back(ColRef{quotients[g]->col(k), qlogs[g]});
+    std::vector<u32> qv;
+    NB_TRYF(merkle_decommit(ctx, first_tree, refs, dpos, qv, first_proof.decommitment.hash_witness, first_proof.decommitment.column_witness));
+    memcpy(first_proof.commitment, first_tree->root, 32);
+  }
+  {
+    Queries lq = queries.fold(1);
+    for (size_t k = 0; k < inner.size(); ++k) {
+      std::vector<u64> pos;
+      NB_TRYF(positions_and_witness(ctx, inner[k].cols, lq.positions, pos, inner_proofs[k].fri_witness));
+      std::vector<std::pair<u32, std::vector<u64>>> dpos{{inner[k].log, pos}};
+      std::vector<ColRef> refs; for (int c = 0; c < 4; ++c) refs.push_back(ColRef{inner[k].cols->col(c), inner[k].log});
+      std::vector<u32> qv;
+      NB_TRYF(merkle_decommit(ctx, inner[k].tree, refs, dpos, qv, inner_proofs[k].decommitment.hash_witness, inner_proofs[k].decommitment.column_witness));
+      memcpy(inner_proofs[k].commitment, inner[k].tree->root, 32);
+      lq = lq.fold(1);
+    }
+  }
+  std::vector<std::vector<u32>> queried_values(4); std::vector<Decommitment> decommitments(4);
+  for (int t = 0; t < 4; ++t) {
+    std::vector<ColRef> refs;
+    for (size_t g = 0; g < s->trees[t].cols.size(); ++g) refs.push_back(ColRef{s->trees[t].lde_ptr(g), s->trees[t].cols[g].log + blow});
+    NB_TRYF(merkle_decommit(ctx, s->trees[t].merkle, refs, by_log, queried_values[t], decommitments[t].hash_witness, decommitments[t].column_witness));
+  }
+  cleanup_fri();
+#undef NB_TRYF
+
+  // ---------------- sanity check: composition(oods) == recomputed from the sampled mask values ----------------
+  {
+    qm31 accumulation = qm31_zero();
+    for (const AirComponent& c : air.comps) {
+      std::vector<qm31> mask(c.masks.size());
+      for (size_t m = 0; m < c.masks.size(); ++m) {
+        const auto& o = offs[c.masks[m].tree][c.masks[m].col];
+        size_t k = std::find(o.begin(), o.end(), c.masks[m].off) - o.begin();
+        mask[m] = sampled[c.masks[m].tree][c.masks[m].col][k];
+      }
+      qm31 dinv = qm31_inv(coset_vanishing_q(c.log_size, oods));
+      std::vector<qm31> br(c.n_base_regs), er(c.n_ext_regs);
+      run_point(c.prog, mask.data(), params, br, er, [&](qm31 v) { accumulation = qm31_add(qm31_mul(accumulation, random_coeff), qm31_mul(dinv, v)); });
+    }
+    qm31 cv[4] = {sampled[3][0][0], sampled[3][1][0], sampled[3][2][0], sampled[3][3][0]};
+    if (!qm31_eq(from_partial_evals(cv), accumulation)) return set_err(ctx, NB200_ERR_CONSTRAINTS, "ConstraintsNotSatisfied");
+  }
+
+  // ---------------- StarkProof -> postcard ----------------
+  Postcard pc;
+  pc.varint(s->pow_bits); pc.varint(s->log_blowup); pc.varint(s->log_last); pc.varint(s->n_queries);
+  pc.varint(4); for (int t = 0; t < 4; ++t) pc.hash(s->trees[t].merkle->root);
+  pc.varint(4);
+  for (int t = 0; t < 4; ++t) { pc.varint(sampled[t].size()); for (auto& c : sampled[t]) { pc.varint(c.size()); for (auto& v : c) pc.q(v); } }
+  pc.varint(4); for (int t = 0; t < 4; ++t) put_decommitment(pc, decommitments[t]);
+  pc.varint(4); for (int t = 0; t < 4; ++t) { pc.varint(queried_values[t].size()); for (u32 v : queried_values[t]) pc.varint(v); }
+  pc.varint(nonce);
+  put_fri_layer(pc, first_proof);
+  pc.varint(inner_proofs.size()); for (auto& l : inner_proofs) put_fri_layer(pc, l);
+  pc.varint(last_layer_poly.size()); for (auto& v : last_layer_poly) pc.q(v);
+  pc.varint(s->log_last);
+  proof_bytes.swap(pc.out);
+  return NB200_OK;
+}
+
+// LogupTraceGenerator over the committed trace (the trace evaluations are passed in by the caller, as in the reference
+// where generate_interaction_trace reads the finalized traces — machine.rs:242-247)
+nb200_status gen_interaction(nb200_ctx* ctx, const AirProgram& air, u32 comp_idx, const nb200_cols* const* tree0, size_t n0, const nb200_cols* const* tree1, size_t n1,
+                             const std::vector<qm31>& params, nb200_cols** out, qm31* claimed) {
+  NB_ARG(ctx, comp_idx < air.comps.size(), "gen_interaction: component index");
+  const AirComponent& c = air.comps[comp_idx];
+  std::vector<std::vector<const u32*>> flat(2);
+  std::vector<std::vector<u32>> flog(2);
+  for (size_t b = 0; b < n0; ++b) for (size_t k = 0; k < tree0[b]->n_cols; ++k) { flat[0].push_back(tree0[b]->col(k)); flog[0].push_back(tree0[b]->log_size); }
+  for (size_t b = 0; b < n1; ++b) for (size_t k = 0; k < tree1[b]->n_cols; ++k) { flat[1].push_back(tree1[b]->col(k)); flog[1].push_back(tree1[b]->log_size); }
+  std::vector<const u32*> mask_cols(c.masks.size(), nullptr);
+  for (size_t m = 0; m < c.masks.size(); ++m) {
+    const AirMask& mk = c.masks[m];
+    if (mk.tree == 2) continue;
+    NB_ARG(ctx, mk.col < flat[mk.tree].size(), "gen_interaction: AIR references a missing trace column");
+    NB_ARG(ctx, flog[mk.tree][mk.col] == c.log_size, "gen_interaction: column size differs from the component's log_size");
+    mask_cols[m] = flat[mk.tree][mk.col];
+  }
+  u32* d_params = nullptr;
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(params.size(), 1) * 16));
+  if (!params.empty()) NB_CUDA(ctx, cudaMemcpyAsync(d_params, params.data(), params.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+  nb200_cols* o = nullptr;
+  NB_TRY(nb200_cols_alloc(ctx, (size_t)4 * c.n_logup_cols(), c.log_size, &o));
+  nb200_status st = logup_generate(ctx, c, mask_cols, d_params, o->d, claimed);
+  cudaStreamSynchronize(ctx->stream);
+  dfree(ctx, d_params);
+  if (st != NB200_OK) { nb200_cols_free(ctx, o); return st; }
+  *out = o;
+  return NB200_OK;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+// ---- Blake2sChannel (stwo core/channel/blake2s.rs) — machine.rs:197-206,240,262 ----
+nb200_status nb200_channel_new(nb200_ctx* ctx, nb200_channel** out) {
+  if (!out) return NB200_ERR_ARG;
+  nb200_channel* c = new nb200_channel();
+  if (ctx) c->ch.draw_domain_sep = ctx->draw_domain_sep;
+  *out = c;
+  return NB200_OK;
+}
+nb200_status nb200_channel_clone(const nb200_channel* c, nb200_channel** out) { if (!c || !out) return NB200_ERR_ARG; *out = new nb200_channel(*c); return NB200_OK; }
+void nb200_channel_free(nb200_channel* c) { delete c; }
+void nb200_channel_digest(const nb200_channel* c, uint8_t out[32]) { memcpy(out, c->ch.digest.data(), 32); }
+void nb200_channel_mix_u64(nb200_channel* c, uint64_t v) { c->ch.mix_u64(v); }
+void nb200_channel_mix_u32s(nb200_channel* c, const uint32_t* w, size_t n) { c->ch.mix_u32s(w, n); }
+void nb200_channel_mix_felts(nb200_channel* c, const uint32_t* felts, size_t n) { c->ch.mix_u32s(felts, 4 * n); }
+void nb200_channel_mix_root(nb200_channel* c, const uint8_t root[32]) { c->ch.mix_root(root); }
+void nb200_channel_draw_felt(nb200_channel* c, uint32_t out[4]) { qm31 q = c->ch.draw_felt(); memcpy(out, q.c, 16); }
+void nb200_channel_draw_felts(nb200_channel* c, size_t n, uint32_t* out) { std::vector<qm31> v(n); c->ch.draw_felts(n, v.data()); if (n) memcpy(out, v.data(), n * 16); }
+void nb200_channel_draw_random_bytes(nb200_channel* c, uint8_t out[32]) { c->ch.draw_random_bytes(out); }
+
+// ---- AIR ----
+nb200_status nb200_air_load(nb200_ctx* ctx, const uint32_t* words, size_t n_words, nb200_air** out) {
+  if (!out) return NB200_ERR_ARG;
+  try { nb200_air* a = new nb200_air(); a->prog = air_parse(words, n_words); *out = a; return NB200_OK; }
+  catch (std::exception& e) { return set_err(ctx, NB200_ERR_ARG, e.what()); }
+}
+void nb200_air_free(nb200_air* a) { delete a; }
+uint32_t nb200_air_n_params(const nb200_air* a) { return a ? a->prog.n_params : 0; }
+uint32_t nb200_air_n_components(const nb200_air* a) { return a ? (uint32_t)a->prog.comps.size() : 0; }
+
+// ---- CommitmentSchemeProver ----
+nb200_status nb200_scheme_new(nb200_ctx* ctx, uint32_t pow_bits, uint32_t log_blowup, uint32_t log_last_layer_degree_bound, uint32_t n_queries, nb200_scheme** out) {
+  if (!ctx || !out) return NB200_ERR_ARG;
+  NB_ARG(ctx, log_blowup >= 1 && log_blowup <= 4 && n_queries >= 1 && log_last_layer_degree_bound <= 10, "scheme: config out of range");
+  nb200_scheme* s = new nb200_scheme();
+  s->ctx = ctx; s->pow_bits = pow_bits; s->log_blowup = log_blowup; s->log_last = log_last_layer_degree_bound; s->n_queries = n_queries;
+  *out = s;
+  return NB200_OK;
+}
+void nb200_scheme_free(nb200_scheme* s) {
+  if (!s) return;
+  for (auto& t : s->trees) free_tree(s->ctx, t);
+  delete s;
+}
+nb200_status nb200_scheme_commit(nb200_scheme* s, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel* channel, uint8_t root[32]) {
+  if (!s || !channel) return NB200_ERR_ARG;
+  return scheme_commit_evals(s, eval_batches, n_batches, channel->ch, root);
+}
+nb200_status nb200_gen_interaction_trace(nb200_ctx* ctx, const nb200_air* air, uint32_t component, const nb200_cols* const* tree0, size_t n0,
+                                         const nb200_cols* const* tree1, size_t n1, const uint32_t* params, size_t n_params,
+                                         nb200_cols** out, uint32_t claimed_sum[4]) {
+  if (!ctx || !air || !out) return NB200_ERR_ARG;
+  std::vector<qm31> p(n_params);
+  if (n_params) memcpy(p.data(), params, n_params * 16);
+  qm31 cs;
+  NB_TRY(gen_interaction(ctx, air->prog, component, tree0, n0, tree1, n1, p, out, &cs));
+  memcpy(claimed_sum, cs.c, 16);
+  return NB200_OK;
+}
+nb200_status nb200_prove(nb200_scheme* s, const nb200_air* air, const uint32_t* params, size_t n_params, nb200_channel* channel,
+                         uint8_t** proof_out, size_t* proof_len) {
+  if (!s || !air || !channel || !proof_out || !proof_len) return NB200_ERR_ARG;
+  std::vector<qm31> p(n_params);
+  if (n_params) memcpy(p.data(), params, n_params * 16);
+  std::vector<uint8_t> bytes;
+  NB_TRY(prove_impl(s, air->prog, p, channel->ch, bytes));
+  uint8_t* o = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
+  memcpy(o, bytes.data(), bytes.size());
+  *proof_out = o; *proof_len = bytes.size();
+  return NB200_OK;
+}
+
+}  // extern "C"

@@ -11,8 +11,9 @@ constraints (range_bool.rs), one LogUp fraction per range-checked byte with one 
 preprocessed column addressed by id, like prover/src/extensions/multiplicity.rs) so that trees hold mixed-size columns.
 With 21 lanes the column counts are 3 / 341 / 1012 — the reference's 27 / 347 / 1012.
 
-`prove(backend, ...)` is written against a small backend protocol so the very same driver runs the CUDA backend
-(nexus_zkvm_b200.prover.CudaBackend) and, in tests only, the oracle.
+`prove(backend, ...)` is written against a small backend protocol (channel / prover.commit / gen_interaction /
+commit_interaction / prove); the product backend is nexus_zkvm_b200.prover.CudaBackend, and the parity tests plug
+their CPU checker into the same driver.
 """
 import numpy as np
 

@@ -1,0 +1,162 @@
+"""ctypes mirror of the proving half of the C ABI (include/nb200.h): Blake2sChannel, AIR, CommitmentSchemeProver,
+interaction-trace generation and stwo::prover::prove — the surface /root/reference prover/src/machine.rs:197-290 drives.
+`CudaBackend` plugs into nexus_zkvm_b200.machine.prove()."""
+import ctypes as C
+
+import numpy as np
+
+from . import Context, Columns, Nb200Error, lib, u32p, u8p
+
+
+class Channel:
+    """Blake2sChannel (host side of the library)."""
+
+    def __init__(self, ctx=None, _h=None):
+        self.ctx = ctx
+        if _h is not None:
+            self._h = _h
+            return
+        self._h = C.c_void_p()
+        st = lib().nb200_channel_new(ctx._h if ctx is not None else None, C.byref(self._h))
+        if st:
+            raise Nb200Error(f"nb200_channel_new failed ({st})")
+
+    def __del__(self):
+        try:
+            lib().nb200_channel_free(self._h)
+        except Exception:
+            pass
+
+    def clone(self):
+        h = C.c_void_p()
+        lib().nb200_channel_clone(self._h, C.byref(h))
+        return Channel(self.ctx, h)
+
+    def digest(self):
+        out = (C.c_uint8 * 32)(); lib().nb200_channel_digest(self._h, out); return bytes(out)
+
+    def mix_u64(self, v):
+        lib().nb200_channel_mix_u64(self._h, C.c_uint64(v))
+
+    def mix_u32s(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        lib().nb200_channel_mix_u32s(self._h, w.ctypes.data_as(u32p), C.c_size_t(w.size))
+
+    def mix_felts(self, felts):
+        f = np.ascontiguousarray(np.asarray(felts, dtype=np.uint32).reshape(-1))
+        lib().nb200_channel_mix_felts(self._h, f.ctypes.data_as(u32p), C.c_size_t(f.size // 4))
+
+    def mix_root(self, root):
+        lib().nb200_channel_mix_root(self._h, (C.c_uint8 * 32).from_buffer_copy(root))
+
+    def draw_felt(self):
+        out = np.zeros(4, np.uint32); lib().nb200_channel_draw_felt(self._h, out.ctypes.data_as(u32p)); return out
+
+    def draw_felts(self, n):
+        out = np.zeros((n, 4), np.uint32); lib().nb200_channel_draw_felts(self._h, C.c_size_t(n), out.ctypes.data_as(u32p)); return out
+
+    def draw_random_bytes(self):
+        out = (C.c_uint8 * 32)(); lib().nb200_channel_draw_random_bytes(self._h, out); return bytes(out)
+
+
+class Air:
+    def __init__(self, ctx, words):
+        self.ctx = ctx
+        self.words = np.ascontiguousarray(words, dtype=np.uint32)
+        self._h = C.c_void_p()
+        ctx._chk(lib().nb200_air_load(ctx._h, self.words.ctypes.data_as(u32p), C.c_size_t(self.words.size), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            lib().nb200_air_free(self._h)
+        except Exception:
+            pass
+
+
+class CommitmentSchemeProver:
+    """CommitmentSchemeProver::<CudaBackend, Blake2sMerkleChannel> + the Machine-level steps that need device data."""
+
+    def __init__(self, ctx, air_words, config):
+        self.ctx, self.config = ctx, config
+        self.air = Air(ctx, air_words)
+        self._h = C.c_void_p()
+        ctx._chk(lib().nb200_scheme_new(ctx._h, C.c_uint32(config["pow_bits"]), C.c_uint32(config["log_blowup"]),
+                                        C.c_uint32(config["log_last"]), C.c_uint32(config["n_queries"]), C.byref(self._h)))
+        self.tree_evals = []  # per committed tree: list of eval batches (kept alive; read by gen_interaction)
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                lib().nb200_scheme_free(self._h)
+        except Exception:
+            pass
+
+    def _batches_from_host(self, cols, coset_order):
+        """Group consecutive equal-length host columns into device batches (commitment order is preserved)."""
+        batches, i = [], 0
+        while i < len(cols):
+            j = i
+            while j < len(cols) and len(cols[j]) == len(cols[i]):
+                j += 1
+            host = np.stack([np.ascontiguousarray(c, dtype=np.uint32) for c in cols[i:j]])
+            batches.append(self.ctx.upload(host, coset_order=coset_order))
+            i = j
+        return batches
+
+    def commit_batches(self, batches, ch):
+        arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+        root = (C.c_uint8 * 32)()
+        self.ctx._chk(lib().nb200_scheme_commit(self._h, arr, C.c_size_t(len(batches)), ch._h, root))
+        self.tree_evals.append(list(batches))
+        return bytes(root)
+
+    def commit(self, cols, ch, coset_order=False):
+        return self.commit_batches(self._batches_from_host(cols, coset_order), ch)
+
+    def gen_interaction(self, comp, log_size, n_logup_cols, params):
+        p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
+        t0, t1 = self.tree_evals[0], self.tree_evals[1]
+        a0 = (C.c_void_p * len(t0))(*[b._h for b in t0])
+        a1 = (C.c_void_p * len(t1))(*[b._h for b in t1])
+        out = C.c_void_p()
+        claimed = np.zeros(4, np.uint32)
+        self.ctx._chk(lib().nb200_gen_interaction_trace(self.ctx._h, self.air._h, C.c_uint32(comp), a0, C.c_size_t(len(t0)), a1, C.c_size_t(len(t1)),
+                                                        p.ctypes.data_as(u32p), C.c_size_t(p.shape[0]), C.byref(out), claimed.ctypes.data_as(u32p)))
+        cols = Columns(self.ctx, out)
+        assert cols.n_cols == 4 * n_logup_cols and cols.log_size == log_size
+        return cols, tuple(int(x) for x in claimed)
+
+    def commit_interaction(self, inter, ch):
+        # `inter` holds device batches straight from gen_interaction: no host round trip
+        return self.commit_batches(list(inter), ch)
+
+    def prove(self, ch, params):
+        p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
+        out = u8p(); ln = C.c_size_t()
+        self.ctx._chk(lib().nb200_prove(self._h, self.air._h, p.ctypes.data_as(u32p), C.c_size_t(p.shape[0]), ch._h, C.byref(out), C.byref(ln)))
+        data = bytes(np.ctypeslib.as_array(out, shape=(max(ln.value, 1),))[:ln.value])
+        lib().nb200_free(C.cast(out, C.c_void_p))
+        return data
+
+
+class CudaBackend:
+    """Backend protocol used by nexus_zkvm_b200.machine.prove (the stand-in for `SimdBackend`)."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or Context(device)
+
+    def channel(self):
+        return Channel(self.ctx)
+
+    def prover(self, words, config):
+        return CommitmentSchemeProver(self.ctx, words, config)
+
+
+def smoke(ctx):
+    """Tiny full prove on the GPU (used by __graft_entry__.smoke); raises on failure."""
+    from . import machine as M
+    m = M.AddMachine(log_size=8, n_lanes=1)
+    cols, mult = m.fill_main_trace(seed=1)
+    proof, claimed, _aux = M.prove(m, CudaBackend(ctx), cols, mult)
+    assert M.verify_claimed_sums(claimed) and len(proof) > 1000
+    return proof
