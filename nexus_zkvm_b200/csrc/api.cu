@@ -6,6 +6,7 @@
 #include <cstring>
 
 namespace nb {
+void fft_drop_tables(nb200_ctx* ctx);
 std::string& global_err() { static std::string e; return e; }
 nb200_status merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const std::vector<ColRef>& cols_in,
                              const std::vector<std::pair<u32, std::vector<u64>>>& queries,
@@ -49,6 +50,7 @@ nb200_status nb200_ctx_create(int device, nb200_ctx** out) {
 void nb200_ctx_destroy(nb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  fft_drop_tables(ctx);
   if (ctx->tw.d_tw) cudaFree(ctx->tw.d_tw);
   if (ctx->tw.d_itw) cudaFree(ctx->tw.d_itw);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

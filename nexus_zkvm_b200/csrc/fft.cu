@@ -8,16 +8,18 @@
 //   ([x, y] -> [y, -y, -x, x]), layers >= 1 use line (x) twiddles; interpolate runs layers 0..n-1 with
 //   ibutterfly and scales by 2^-n, evaluate runs n-1..0 with butterfly on zero-extended coefficients.
 //
-// Kernel structure (HBM-bound integer work, no tensor cores):
+// Kernel structure (integer work bounded by HBM traffic and INT32 issue, no tensor cores):
 //   A transform of 2^n is split into passes of <= 13 layers.  A pass owns a contiguous range of layers
 //   [lo, lo+L); each CTA stages a tile of 2^T words (2^L "rows" x 2^W contiguous words, W = T-L) of CB columns
-//   into shared memory with coalesced accesses, runs the L layers there in rounds of <= 4 layers (every
+//   into shared memory with coalesced 128-bit accesses, runs the L layers there in rounds of <= 4 layers (every
 //   thread holds 16 words in registers: a radix-16 butterfly network per round), and writes the tile back.
-//   Twiddles of a round are loaded once into registers and reused for the CB columns of the CTA.
-//   Shared memory is XOR-swizzled (s ^ ((s >> 4) & 31)) which makes every round and the staging
-//   conflict-free (verified exhaustively by tests/test_layout.py).
+//   Twiddles of a round are fetched with vector loads into registers and reused for the CB columns of the CTA.
+//   Shared memory is XOR-swizzled; tests/test_layout.py proves every access pattern conflict-free.
+//   `fft_tile_kernel<INV,T,W>` is the compile-time specialised fast path; `fft_pass_kernel` is the generic
+//   fallback for shapes outside the specialised set.
 #include "common.cuh"
 #include "circle_host.h"
+#include <map>
 
 namespace nb {
 
@@ -27,6 +29,7 @@ struct FftPass {
   size_t src_stride, dst_stride;
   size_t src_len;     // valid words per source column
   const u32* tw;      // twiddle (or inverse twiddle) bank
+  const u32* ctw;     // circle (layer 0) twiddles of this transform size, 2^(n-1) words
   u32 tw_len;         // bank length (2^k)
   u32 n_cols;
   u32 n;              // log size of the transform
@@ -36,8 +39,6 @@ struct FftPass {
   u32 scale;          // multiply outputs by this (interpolate last pass) if apply_scale
   u32 apply_scale;
 };
-
-__device__ __forceinline__ u32 swz(u32 s) { return s ^ ((s >> 4) & 31u); }
 
 __device__ __forceinline__ void butterfly(u32& v0, u32& v1, u32 t) {
   u32 tmp = m31_mul(v1, t);
@@ -62,6 +63,158 @@ __device__ __forceinline__ u32 circle_tw(const u32* __restrict__ tw, u32 tw_len,
   u32 v = (r < 2) ? y : x;
   return (r == 1 || r == 2) ? (P31 - v) : v;
 }
+__global__ void circle_table_kernel(const u32* __restrict__ tw, u32 tw_len, u32 n, u32* __restrict__ out) {
+  u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < (1u << (n - 1))) out[h] = circle_tw(tw, tw_len, n, h);
+}
+
+// =====================================================================================================
+// fast path: compile-time tile shape
+// =====================================================================================================
+// swizzle keeps aligned groups of 4 words intact (128-bit accesses) and is conflict-free for: 128-bit staging,
+// the 128-bit round at bit 0, and the 32-bit rounds at every bit position used by the schedules below.
+__device__ __forceinline__ u32 swz2(u32 s) { return s ^ (((s >> 5) & 3u) << 2) ^ (((s >> 8) & 1u) << 4); }
+
+template <bool INV>
+__device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const int jlo) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = INV ? jj : 3 - jj;
+    if (j >= jlo) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
+        const int k1 = k0 | (1 << j);
+        const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
+        if (INV) ibutterfly(v[k0], v[k1], tw[off]);
+        else butterfly(v[k0], v[k1], tw[off]);
+      }
+    }
+  }
+}
+
+template <bool INV, int T, int W, int CB>
+__global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kernel(const FftPass p) {
+  extern __shared__ __align__(16) u32 sm[];
+  constexpr int L = T - W;
+  constexpr int NT = 1 << (T - 4);
+  constexpr int NFULL = L / 4, REM = L % 4, NROUNDS = NFULL + (REM ? 1 : 0);
+  const u32 lo = p.lo, n = p.n;
+  const u32 tid = threadIdx.x;
+  const u32 tile = blockIdx.x;
+  const u32 mid_bits = W ? lo - W : 0;
+  const u32 tile_mid = tile & ((1u << mid_bits) - 1u);
+  const u32 tile_hi = tile >> mid_bits;
+  const size_t gbase = ((size_t)tile_hi << (lo + L)) | ((size_t)tile_mid << W);
+  const u32 col0 = blockIdx.y * CB;
+  const u32 ncb = min((u32)CB, p.n_cols - col0);
+
+  // ---- stage in: 128-bit coalesced global loads -> swizzled shared
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    if (c < (int)ncb) {
+      const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const u32 s = (tid + it * NT) * 4;
+        const size_t g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g < p.src_len) v = __ldg(reinterpret_cast<const uint4*>(scol + g));
+        *reinterpret_cast<uint4*>(sm + (c << T) + swz2(s)) = v;
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int rr = 0; rr < NROUNDS; ++rr) {
+    const int ri = INV ? rr : NROUNDS - 1 - rr;
+    const int b = ri < NFULL ? W + 4 * ri : T - 4;
+    const int jlo = ri < NFULL ? 0 : 4 - REM;
+    const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
+    // twiddles: layer j of the round is global layer i = lo + b + j - W; the (8 >> j) twiddles of a thread are contiguous
+    u32 tw[15];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= jlo) {
+        const u32 i = lo + b + j - W;
+        const u32 hbase = (tile_hi << (L - (b + j - W) - 1)) | (tau_hi << (3 - j));
+        const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw + hbase) : (p.tw + (p.tw_len - (1u << (n - i))) + hbase);
+        if (j == 0) {
+          uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c4 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+          tw[0] = a.x; tw[1] = a.y; tw[2] = a.z; tw[3] = a.w; tw[4] = c4.x; tw[5] = c4.y; tw[6] = c4.z; tw[7] = c4.w;
+        } else if (j == 1) {
+          uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+          tw[8] = a.x; tw[9] = a.y; tw[10] = a.z; tw[11] = a.w;
+        } else if (j == 2) {
+          uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+          tw[12] = a.x; tw[13] = a.y;
+        } else {
+          tw[14] = __ldg(src);
+        }
+      }
+    }
+    const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
+    if (b == 0) {
+      // the 16 words of a thread are contiguous: 4 x 128-bit shared accesses
+      const u32 a0 = swz2(sbase), a1 = swz2(sbase | 4u), a2 = swz2(sbase | 8u), a3 = swz2(sbase | 12u);
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        if (c < (int)ncb) {
+          u32* smc = sm + (c << T);
+          u32 v[16];
+          uint4 q0 = *reinterpret_cast<uint4*>(smc + a0), q1 = *reinterpret_cast<uint4*>(smc + a1);
+          uint4 q2 = *reinterpret_cast<uint4*>(smc + a2), q3 = *reinterpret_cast<uint4*>(smc + a3);
+          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+          v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w; v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
+          radix16<INV>(v, tw, jlo);
+          *reinterpret_cast<uint4*>(smc + a0) = make_uint4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<uint4*>(smc + a1) = make_uint4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<uint4*>(smc + a2) = make_uint4(v[8], v[9], v[10], v[11]);
+          *reinterpret_cast<uint4*>(smc + a3) = make_uint4(v[12], v[13], v[14], v[15]);
+        }
+      }
+    } else {
+      u32 addr[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) addr[k] = swz2(sbase | ((u32)k << b));
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        if (c < (int)ncb) {
+          u32* smc = sm + (c << T);
+          u32 v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = smc[addr[k]];
+          radix16<INV>(v, tw, jlo);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) smc[addr[k]] = v[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- stage out
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    if (c < (int)ncb) {
+      u32* __restrict__ dcol = p.dst + (size_t)(col0 + c) * p.dst_stride;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const u32 s = (tid + it * NT) * 4;
+        const size_t g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+        uint4 v = *reinterpret_cast<const uint4*>(sm + (c << T) + swz2(s));
+        if (p.apply_scale) { v.x = m31_mul(v.x, p.scale); v.y = m31_mul(v.y, p.scale); v.z = m31_mul(v.z, p.scale); v.w = m31_mul(v.w, p.scale); }
+        *reinterpret_cast<uint4*>(dcol + g) = v;
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// generic fallback (runtime tile shape)
+// =====================================================================================================
+__device__ __forceinline__ u32 swz(u32 s) { return s ^ ((s >> 4) & 31u); }
 
 template <bool INV>
 __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
@@ -79,7 +232,6 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
   const u32 ncb = min(p.cb, p.n_cols - col0);
   const u32 tile_words = 1u << T;
 
-  // ---- stage in: coalesced global -> swizzled shared
   for (u32 c = 0; c < ncb; ++c) {
     const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
     u32* smc = sm + ((size_t)c << T);
@@ -98,7 +250,6 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
     u32 b, jlo;
     if (ri < nfull) { b = W + 4 * ri; jlo = 0; } else { b = T - 4; jlo = 4 - rem; }
     const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
-    // twiddles of this round: layer j (register bit) <-> global layer i = lo + b + j - W
     u32 tw[15];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -138,7 +289,6 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
     __syncthreads();
   }
 
-  // ---- stage out
   for (u32 c = 0; c < ncb; ++c) {
     u32* __restrict__ dcol = p.dst + (size_t)(col0 + c) * p.dst_stride;
     const u32* smc = sm + ((size_t)c << T);
@@ -151,7 +301,7 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
   }
 }
 
-// Generic small transform (n <= 12): one CTA per column, whole column in shared memory, layer by layer.
+// Generic small transform (n <= 8): one CTA per column, whole column in shared memory, layer by layer.
 struct FftSmall {
   const u32* src; u32* dst; size_t src_stride, dst_stride, src_len;
   const u32* tw; u32 tw_len; u32 n_cols, n;
@@ -217,22 +367,81 @@ nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, s
   return NB200_OK;
 }
 
+// ---- circle-twiddle tables (layer 0 of each transform size), cached per ctx ----
+struct CircleTables { std::map<u32, std::pair<u32*, u32*>> by_log; u32 bank_log = 0; };
+static std::map<nb200_ctx*, CircleTables>& circle_cache() { static std::map<nb200_ctx*, CircleTables> m; return m; }
+void fft_drop_tables(nb200_ctx* ctx) {
+  auto it = circle_cache().find(ctx);
+  if (it == circle_cache().end()) return;
+  for (auto& kv : it->second.by_log) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  circle_cache().erase(it);
+}
+static nb200_status circle_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv) {
+  CircleTables& ct = circle_cache()[ctx];
+  if (ct.bank_log != ctx->tw.half_log) {  // the bank was rebuilt: tables stay valid (they hold values, not pointers)
+    ct.bank_log = ctx->tw.half_log;
+  }
+  auto it = ct.by_log.find(n);
+  if (it == ct.by_log.end()) {
+    u32 *f = nullptr, *g = nullptr;
+    size_t len = (size_t)1 << (n - 1);
+    NB_CUDA(ctx, cudaMalloc(&f, len * 4));
+    NB_CUDA(ctx, cudaMalloc(&g, len * 4));
+    u32 thr = 256, blk = (u32)((len + thr - 1) / thr);
+    circle_table_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_tw, 1u << ctx->tw.half_log, n, f);
+    NB_LAUNCH_CHECK(ctx);
+    circle_table_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_itw, 1u << ctx->tw.half_log, n, g);
+    NB_LAUNCH_CHECK(ctx);
+    it = ct.by_log.emplace(n, std::make_pair(f, g)).first;
+  }
+  *fwd = it->second.first; *inv = it->second.second;
+  return NB200_OK;
+}
+
 // ---- pass planning ----
 struct PassPlan { u32 lo, T, W; };
 static void plan_passes(u32 n, std::vector<PassPlan>& out) {
-  // contiguous pass over the low layers, then strided passes (tile rows x 2^W contiguous words)
+  // contiguous pass over the low layers, then strided passes (tile rows x 2^W contiguous words, W >= 4)
   out.clear();
-  u32 LA = n <= 13 ? n : (n >= 21 ? 13 : 12);
+  if (n <= 13) { out.push_back(PassPlan{0, n, 0}); return; }
+  u32 rest_min = n - 13;                      // layers left if the contiguous pass takes 13
+  u32 npass = (rest_min + 8) / 9;             // strided passes of <= 9 layers
+  u32 LA = n - npass * 8;                     // give the strided passes 8 layers each when possible
+  if (LA < 9) LA = 9;
+  if (LA > 13) LA = 13;
   out.push_back(PassPlan{0, LA, 0});
-  u32 rest = n - LA;
-  if (rest == 0) return;
-  u32 npass = (rest + 7) / 8;
-  u32 lo = LA;
+  u32 rest = n - LA, lo = LA;
   for (u32 k = 0; k < npass; ++k) {
     u32 L = rest / npass + (k < rest % npass ? 1 : 0);
-    out.push_back(PassPlan{lo, 12, 12 - L});
+    if (L == 9) out.push_back(PassPlan{lo, 13, 4});
+    else out.push_back(PassPlan{lo, 12, 12 - L});
     lo += L;
   }
+}
+
+template <bool INV, int T, int W, int CB>
+static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
+  constexpr int threads = 1 << (T - 4);
+  constexpr size_t smem = (size_t)CB << (T + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_kernel<INV, T, W, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB - 1) / CB));
+  fft_tile_kernel<INV, T, W, CB><<<grid, threads, smem, ctx->stream>>>(p);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
+// returns true if a specialised kernel exists for (T, W)
+template <bool INV>
+static bool launch_fast(nb200_ctx* ctx, const FftPass& p, nb200_status* st) {
+#define NB_CASE(TT, WW, CBB) if (p.T == TT && p.W == WW) { *st = launch_tile<INV, TT, WW, CBB>(ctx, p); return true; }
+  NB_CASE(9, 0, 4) NB_CASE(10, 0, 4) NB_CASE(11, 0, 4) NB_CASE(12, 0, 4) NB_CASE(13, 0, 2)
+  NB_CASE(12, 4, 4) NB_CASE(12, 5, 4) NB_CASE(12, 6, 4) NB_CASE(12, 7, 4) NB_CASE(12, 8, 4) NB_CASE(13, 4, 2)
+#undef NB_CASE
+  return false;
 }
 
 template <bool INV>
@@ -242,11 +451,18 @@ static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* s
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = src_len;
   p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
   p.tw_len = 1u << ctx->tw.half_log;
+  const u32 *cf = nullptr, *ci = nullptr;
+  NB_TRY(circle_tables(ctx, n, &cf, &ci));
+  p.ctw = INV ? ci : cf;
   p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
   p.cb = pl.T >= 13 ? 2 : 4;
   if (p.cb > n_cols) p.cb = (u32)n_cols;
   p.scale = 0; p.apply_scale = 0;
   if (scale) { p.apply_scale = 1; p.scale = m31_inv((u32)(1u << n) % P31); }
+  // 128-bit staging needs 16-byte aligned columns
+  bool aligned = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15u) == 0 && (src_stride % 4 == 0) && (dst_stride % 4 == 0) && (src_len % 4 == 0);
+  nb200_status st = NB200_OK;
+  if (aligned && launch_fast<INV>(ctx, p, &st)) return st;
   u32 threads = 1u << (pl.T - 4);
   size_t smem = (size_t)p.cb << (pl.T + 2);
   dim3 grid(1u << (n - pl.T), (u32)((n_cols + p.cb - 1) / p.cb));
