@@ -75,8 +75,28 @@ __global__ void circle_table_kernel(const u32* __restrict__ tw, u32 tw_len, u32 
 // the 128-bit round at bit 0, and the 32-bit rounds at every bit position used by the schedules below.
 __device__ __forceinline__ u32 swz2(u32 s) { return s ^ (((s >> 5) & 3u) << 2) ^ (((s >> 8) & 1u) << 4); }
 
+// a * t mod P with the twiddle pre-doubled (t2 = 2t < 2^32): the 64-bit product a * t2 has (a*t) >> 31 in its high
+// word and 2 * ((a*t) mod 2^31) in its low word, so the Mersenne fold is one shifted add (LEA.HI) and one min — the
+// mask and the funnel shift of the plain form disappear, which matters because the ALU pipe is the binding one.
+__device__ __forceinline__ u32 m31_mul_dbl(u32 a, u32 t2) {
+  u64 p = (u64)a * t2;
+  u32 s = ((u32)p >> 1) + (u32)(p >> 32);
+  return umin32(s, s - P31);
+}
+__device__ __forceinline__ void butterfly_dbl(u32& v0, u32& v1, u32 t2) {
+  u32 tmp = m31_mul_dbl(v1, t2);
+  v1 = m31_sub(v0, tmp);
+  v0 = m31_add(v0, tmp);
+}
+__device__ __forceinline__ void ibutterfly_dbl(u32& v0, u32& v1, u32 it2) {
+  u32 tmp = v0;
+  v0 = m31_add(tmp, v1);
+  v1 = m31_mul_dbl(m31_sub(tmp, v1), it2);
+}
+
 template <bool INV>
 __device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const int jlo) {
+  // tw holds DOUBLED twiddles
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const int j = INV ? jj : 3 - jj;
@@ -86,8 +106,8 @@ __device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const
         const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
         const int k1 = k0 | (1 << j);
         const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
-        if (INV) ibutterfly(v[k0], v[k1], tw[off]);
-        else butterfly(v[k0], v[k1], tw[off]);
+        if (INV) ibutterfly_dbl(v[k0], v[k1], tw[off]);
+        else butterfly_dbl(v[k0], v[k1], tw[off]);
       }
     }
   }
@@ -133,7 +153,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
     const int jlo = ri < NFULL ? 0 : 4 - REM;
     const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
     // twiddles: layer j of the round is global layer i = lo + b + j - W; the (8 >> j) twiddles of a thread are contiguous
-    u32 tw[15];
+    u32 tw[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j >= jlo) {
@@ -154,6 +174,9 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
         }
       }
     }
+    // pre-double (see m31_mul_dbl); entries of layers below jlo are never read
+#pragma unroll
+    for (int q = 0; q < 15; ++q) tw[q] = tw[q] << 1;
     const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
     if (b == 0) {
       // the 16 words of a thread are contiguous: 4 x 128-bit shared accesses
@@ -204,7 +227,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
         const u32 s = (tid + it * NT) * 4;
         const size_t g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
         uint4 v = *reinterpret_cast<const uint4*>(sm + (c << T) + swz2(s));
-        if (p.apply_scale) { v.x = m31_mul(v.x, p.scale); v.y = m31_mul(v.y, p.scale); v.z = m31_mul(v.z, p.scale); v.w = m31_mul(v.w, p.scale); }
+        if (p.apply_scale) { const u32 sc2 = p.scale << 1; v.x = m31_mul_dbl(v.x, sc2); v.y = m31_mul_dbl(v.y, sc2); v.z = m31_mul_dbl(v.z, sc2); v.w = m31_mul_dbl(v.w, sc2); }
         *reinterpret_cast<uint4*>(dcol + g) = v;
       }
     }

@@ -121,9 +121,9 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
         ch.mix_u64(ls)
     prover = backend.prover(machine.words, config)
     # tree 0: preprocessed (machine.rs:208-228)
-    prover.commit(machine.preprocessed_columns(), ch, coset_order=True)
+    roots = [prover.commit(machine.preprocessed_columns(), ch, coset_order=True)]
     # tree 1: main trace + extension main columns (machine.rs:230-237)
-    prover.commit(list(main_cols) + [mult], ch, coset_order=True)
+    roots.append(prover.commit(list(main_cols) + [mult], ch, coset_order=True))
     # lookup elements (machine.rs:239-240)
     params = [(0, 0, 0, 0)] * air.n_params
     machine.range256.draw(ch, params)
@@ -136,8 +136,9 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
         inv_n = F.m31_inv((1 << comp.log_size) % P)
         params[comp.cumsum_shift_param] = F.qm31_mul_m31(cs, inv_n)
     ch.mix_felts(claimed)
-    prover.commit_interaction(inter, ch)
-    aux = {"channel_at_prove": ch.clone(), "params": params}
+    roots.append(prover.commit_interaction(inter, ch))
+    aux = {"channel_at_prove": ch.clone(), "params": params, "roots": roots, "log_sizes": log_sizes,
+           "associated_data": bytes(associated_data)}
     proof = prover.prove(ch, params)
     return proof, claimed, aux
 
