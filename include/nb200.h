@@ -104,6 +104,10 @@ nb200_status nb200_merkle_decommit(nb200_ctx*, const nb200_tree*, const nb200_co
                                    uint8_t** hash_witness, size_t* n_hashes,
                                    uint32_t** column_witness, size_t* n_column_witness);
 void nb200_free(void*);
+/* Blake2sMerkleHasher::hash_node on the host: H(left || right || values) with the selected construction (0 or 1, see
+ * nb200_set_flavor); left/right both NULL for leaves.  Used to combine the Merkle caps of row-sharded sub-trees that
+ * the ranks all-gather over NCCL and by a verifier-side shim. */
+nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t* right, const uint32_t* values, size_t n_values, uint8_t out[32]);
 
 /* ---- fused commitment: TreeBuilder::extend_evals + commit (machine.rs:208-263) ---------------------- */
 /* In: evaluation batches (read only).  Out, per batch: the coefficient batch (interpolate) and the LDE batch

@@ -2,10 +2,19 @@
 // nb200_ctx_create fails with NB200_ERR_NO_DEVICE.
 #include "common.cuh"
 #include "circle_host.h"
+#include "blake2s.cuh"
 #include <cstdlib>
 #include <cstring>
 
+#include <chrono>
 namespace nb {
+void trace_mark(nb200_ctx* ctx, const char* stage) {
+  if (!ctx || !ctx->trace) return;
+  cudaStreamSynchronize(ctx->stream);
+  double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (stage) fprintf(stderr, "[nb200] %-28s %9.3f ms\n", stage, now - ctx->trace_t0);
+  ctx->trace_t0 = now;
+}
 void fft_drop_tables(nb200_ctx* ctx);
 std::string& global_err() { static std::string e; return e; }
 nb200_status merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const std::vector<ColRef>& cols_in,
@@ -36,6 +45,7 @@ nb200_status nb200_ctx_create(int device, nb200_ctx** out) {
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { global_err() = cudaGetErrorString(e); delete ctx; return NB200_ERR_CUDA; }
   ctx->own_stream = true;
+  { const char* t = getenv("NB200_TRACE"); ctx->trace = (t && t[0] && t[0] != '0') ? 1 : 0; }
   {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -234,6 +244,34 @@ nb200_status nb200_merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const
   return NB200_OK;
 }
 void nb200_free(void* p) { free(p); }
+
+// Blake2sMerkleHasher::hash_node on the host (cap combination of row-sharded trees, verifier-side use in a shim)
+nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t* right, const uint32_t* values, size_t n_values, uint8_t out[32]) {
+  if ((left == nullptr) != (right == nullptr) || !out || (n_values && !values)) return NB200_ERR_ARG;
+  if (merkle_hash == 0) {
+    u32 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 m[16];
+    if (left) {
+      for (int i = 0; i < 8; ++i) {
+        m[i] = (u32)left[4 * i] | ((u32)left[4 * i + 1] << 8) | ((u32)left[4 * i + 2] << 16) | ((u32)left[4 * i + 3] << 24);
+        m[8 + i] = (u32)right[4 * i] | ((u32)right[4 * i + 1] << 8) | ((u32)right[4 * i + 2] << 16) | ((u32)right[4 * i + 3] << 24);
+      }
+      b2s_compress(h, m, 0, 0, 0, 0);
+    }
+    for (size_t i = 0; i < n_values; i += 16) {
+      for (size_t j = 0; j < 16; ++j) m[j] = i + j < n_values ? values[i + j] : 0u;
+      b2s_compress(h, m, 0, 0, 0, 0);
+    }
+    for (int i = 0; i < 8; ++i) { out[4 * i] = h[i] & 0xff; out[4 * i + 1] = (h[i] >> 8) & 0xff; out[4 * i + 2] = (h[i] >> 16) & 0xff; out[4 * i + 3] = (h[i] >> 24) & 0xff; }
+    return NB200_OK;
+  }
+  if (merkle_hash != 1) return NB200_ERR_ARG;
+  Blake2sHost b;
+  if (left) { b.update(left, 32); b.update(right, 32); }
+  for (size_t i = 0; i < n_values; ++i) { uint8_t le[4] = {(uint8_t)values[i], (uint8_t)(values[i] >> 8), (uint8_t)(values[i] >> 16), (uint8_t)(values[i] >> 24)}; b.update(le, 4); }
+  b.finalize(out);
+  return NB200_OK;
+}
 
 // ---- fused commitment ----
 nb200_status nb200_commit_evals(nb200_ctx* ctx, const nb200_cols* const* eval_batches, size_t n_batches, uint32_t log_blowup,

@@ -27,6 +27,8 @@ struct nb200_ctx {
   nb::TwiddleBank tw;
   int merkle_hash = 0, draw_domain_sep = 0, pow_variant = 0;
   uint64_t launches = 0;
+  int trace = 0;          // NB200_TRACE=1: per-stage wall clock (after a stream sync) on stderr
+  double trace_t0 = 0;
   // scratch for small device->host transfers
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
@@ -85,6 +87,9 @@ std::string& global_err();
     nb200_status _s = (expr);                 \
     if (_s != NB200_OK) return _s;            \
   } while (0)
+
+// NB200_TRACE stage timer: prints the time since the previous mark (stream drained first)
+void trace_mark(nb200_ctx* ctx, const char* stage);
 
 // Stream-ordered device allocation from the device's default memory pool (release threshold raised at ctx
 // creation, so steady-state alloc/free never reaches the driver).

@@ -76,6 +76,7 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
   u32 max_log = 0;
   for (size_t b = 0; b < n; ++b) max_log = std::max(max_log, evals[b]->log_size + s->log_blowup);
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
+  trace_mark(ctx, nullptr);
   SchemeTree t;
   for (size_t b = 0; b < n; ++b) {
     nb200_cols *co = nullptr, *lde = nullptr;
@@ -86,8 +87,10 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
     NB_TRY(fft_interpolate(ctx, evals[b]->d, co->d, co->n_cols, co->log_size));
     NB_TRY(fft_evaluate(ctx, co->d, co->log_size, lde->d, lde->log_size, co->n_cols));
   }
+  trace_mark(ctx, "commit: ifft+lde");
   nb200_status st = finish_tree(ctx, t, ch);
   if (st != NB200_OK) { free_tree(ctx, t); return st; }
+  trace_mark(ctx, "commit: merkle");
   if (root) memcpy(root, t.merkle->root, 32);
   s->trees.push_back(std::move(t));
   return NB200_OK;
@@ -205,6 +208,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
   NB_ARG(ctx, params.size() == air.n_params, "prove: parameter table size");
   const u32 blow = s->log_blowup;
 
+  trace_mark(ctx, nullptr);
   // ---------------- composition polynomial ----------------
   qm31 random_coeff = ch.draw_felt();
   size_t n_total = 0; u32 comp_log = 0;
@@ -257,6 +261,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
     free_ext();
     if (st != NB200_OK) { free_acc(); dfree(ctx, d_params); return st; }
   }
+  trace_mark(ctx, "constraint quotients");
   // DomainEvaluationAccumulator::finalize: fold the per-size accumulators upwards
   nb200_cols* cur = nullptr;  // coefficients of the running composition (4 columns)
   for (auto& kv : acc) {
@@ -285,6 +290,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
     s->trees.push_back(std::move(t));
   }
 
+  trace_mark(ctx, "composition commit");
   // ---------------- OODS sampling ----------------
   qpoint oods;
   {
@@ -339,6 +345,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
     ch.mix_felts(flat.data(), flat.size());
   }
 
+  trace_mark(ctx, "oods eval_at_point");
   // ---------------- DEEP quotients ----------------
   qm31 q_coeff = ch.draw_felt();
   struct CRef { int t; size_t g; u32 log; };
@@ -396,6 +403,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
     i = j;
   }
 
+  trace_mark(ctx, "deep quotients");
   // ---------------- FRI commit phase ----------------
   struct Layer { nb200_cols* cols; nb200_tree* tree; u32 log; };
   std::vector<Layer> inner;
@@ -472,6 +480,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
     ch.mix_felts(last_layer_poly.data(), last_layer_poly.size());
   }
 
+  trace_mark(ctx, "fri commit");
   // ---------------- proof of work, queries, decommitments ----------------
   uint64_t nonce = 0;
   NB_TRYF(grind(ctx, ch.digest.data(), s->pow_bits, &nonce));
@@ -517,6 +526,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
   cleanup_fri();
 #undef NB_TRYF
 
+  trace_mark(ctx, "pow + decommit");
   // ---------------- sanity check: composition(oods) == recomputed from the sampled mask values ----------------
   {
     qm31 accumulation = qm31_zero();
@@ -549,6 +559,7 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
   pc.varint(last_layer_poly.size()); for (auto& v : last_layer_poly) pc.q(v);
   pc.varint(s->log_last);
   proof_bytes.swap(pc.out);
+  trace_mark(ctx, "sanity + serialize");
   return NB200_OK;
 }
 
@@ -575,7 +586,9 @@ nb200_status gen_interaction(nb200_ctx* ctx, const AirProgram& air, u32 comp_idx
   if (!params.empty()) NB_CUDA(ctx, cudaMemcpyAsync(d_params, params.data(), params.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
   nb200_cols* o = nullptr;
   NB_TRY(nb200_cols_alloc(ctx, (size_t)4 * c.n_logup_cols(), c.log_size, &o));
+  trace_mark(ctx, nullptr);
   nb200_status st = logup_generate(ctx, c, mask_cols, d_params, o->d, claimed);
+  trace_mark(ctx, "logup interaction trace");
   cudaStreamSynchronize(ctx->stream);
   dfree(ctx, d_params);
   if (st != NB200_OK) { nb200_cols_free(ctx, o); return st; }

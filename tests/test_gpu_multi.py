@@ -1,0 +1,63 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the NCCL column-sharded -> all-to-all -> row-sharded
+commit of nexus_zkvm_b200.parallel reproduces the single-GPU Merkle root bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = (1 << 31) - 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_cols, log_size, q):
+    import torch
+    import torch.distributed as dist
+    import nexus_zkvm_b200 as nb
+    from nexus_zkvm_b200 import parallel as par
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ctx = nb.Context(rank, stream=torch.cuda.current_stream().cuda_stream)
+        rng = np.random.default_rng(7)
+        full = rng.integers(0, P, (n_cols, 1 << log_size), dtype=np.uint32)
+        lo, hi = par.column_ranges(n_cols, world)[rank]
+        mine = torch.from_numpy(full[lo:hi].view(np.int32).copy()).cuda()
+        root, rows, caps = par.sharded_commit(par.CudaEngine(ctx), dist, mine, n_cols, log_size, 1)
+        single = None
+        if rank == 0:
+            ev = ctx.upload(full)
+            _, _, tree = ctx.commit_evals([ev], 1)
+            single = tree.root
+        q.put((rank, root, single))
+        torch.cuda.synchronize()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cols,log_size", [(50, 12), (1386, 14)])
+def test_sharded_commit_matches_single_gpu_root(n_cols, log_size):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_cols, log_size, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = [s for _, _, s in res if s is not None][0]
+    for rank, root, _ in res:
+        assert root == single, f"rank {rank}"
