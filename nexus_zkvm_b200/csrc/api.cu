@@ -63,6 +63,8 @@ void nb200_ctx_destroy(nb200_ctx* ctx) {
   fft_drop_tables(ctx);
   if (ctx->tw.d_tw) cudaFree(ctx->tw.d_tw);
   if (ctx->tw.d_itw) cudaFree(ctx->tw.d_itw);
+  if (ctx->tw.d_tw2) cudaFree(ctx->tw.d_tw2);
+  if (ctx->tw.d_itw2) cudaFree(ctx->tw.d_itw2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

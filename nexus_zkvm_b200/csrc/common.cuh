@@ -14,6 +14,8 @@ struct TwiddleBank {
   u32 half_log = 0;       // log size k of the root half coset; buffers hold 2^k words
   u32* d_tw = nullptr;    // x-coordinates, layer l at offset 2^k - 2^(k-l), bit-reversed within the layer
   u32* d_itw = nullptr;   // element-wise inverses
+  u32* d_tw2 = nullptr;   // 2 * twiddle (< 2^32): the FFT's Mersenne multiply wants the doubled constant (m31_mul_dbl)
+  u32* d_itw2 = nullptr;  // 2 * inverse twiddle
 };
 
 }  // namespace nb

@@ -29,7 +29,8 @@ struct FftPass {
   size_t src_stride, dst_stride;
   size_t src_len;     // valid words per source column
   const u32* tw;      // twiddle (or inverse twiddle) bank
-  const u32* ctw;     // circle (layer 0) twiddles of this transform size, 2^(n-1) words
+  const u32* tw2;     // the same bank doubled (2t), for m31_mul_dbl
+  const u32* ctw2;    // DOUBLED circle (layer 0) twiddles of this transform size, 2^(n-1) words
   u32 tw_len;         // bank length (2^k)
   u32 n_cols;
   u32 n;              // log size of the transform
@@ -65,7 +66,7 @@ __device__ __forceinline__ u32 circle_tw(const u32* __restrict__ tw, u32 tw_len,
 }
 __global__ void circle_table_kernel(const u32* __restrict__ tw, u32 tw_len, u32 n, u32* __restrict__ out) {
   u32 h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < (1u << (n - 1))) out[h] = circle_tw(tw, tw_len, n, h);
+  if (h < (1u << (n - 1))) out[h] = circle_tw(tw, tw_len, n, h) << 1;  // doubled, see m31_mul_dbl
 }
 
 // =====================================================================================================
@@ -129,6 +130,14 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
   const u32 col0 = blockIdx.y * CB;
   const u32 ncb = min((u32)CB, p.n_cols - col0);
 
+  // ---- staging geometry: thread `tid` moves the 4 x uint4 at s_it = (tid + it*NT)*4.  For NT*4 >= 512 the swizzle
+  // bits (5, 6, 8) are not touched by `it`, so physical and global offsets are affine in `it` (no per-access math).
+  constexpr bool AFFINE = (NT * 4 >= 512) && (W <= T - 2);
+  const u32 s0 = tid * 4;
+  const u32 phys0 = swz2(s0);
+  const size_t g0 = W ? (gbase | ((size_t)(s0 >> W) << lo) | (s0 & ((1u << W) - 1u))) : (gbase | s0);
+  const size_t gstep = W ? ((size_t)((NT * 4) >> W) << lo) : (size_t)(NT * 4);
+
   // ---- stage in: 128-bit coalesced global loads -> swizzled shared
 #pragma unroll
   for (int c = 0; c < CB; ++c) {
@@ -136,11 +145,16 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
       const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const u32 s = (tid + it * NT) * 4;
-        const size_t g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+        u32 ph; size_t g;
+        if (AFFINE) { ph = phys0 + it * NT * 4; g = g0 + it * gstep; }
+        else {
+          const u32 s = (tid + it * NT) * 4;
+          ph = swz2(s);
+          g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+        }
         uint4 v = make_uint4(0, 0, 0, 0);
         if (g < p.src_len) v = __ldg(reinterpret_cast<const uint4*>(scol + g));
-        *reinterpret_cast<uint4*>(sm + (c << T) + swz2(s)) = v;
+        *reinterpret_cast<uint4*>(sm + (c << T) + ph) = v;
       }
     }
   }
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
       if (j >= jlo) {
         const u32 i = lo + b + j - W;
         const u32 hbase = (tile_hi << (L - (b + j - W) - 1)) | (tau_hi << (3 - j));
-        const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw + hbase) : (p.tw + (p.tw_len - (1u << (n - i))) + hbase);
+        const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw2 + hbase) : (p.tw2 + (p.tw_len - (1u << (n - i))) + hbase);
         if (j == 0) {
           uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c4 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
           tw[0] = a.x; tw[1] = a.y; tw[2] = a.z; tw[3] = a.w; tw[4] = c4.x; tw[5] = c4.y; tw[6] = c4.z; tw[7] = c4.w;
@@ -174,9 +188,6 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
         }
       }
     }
-    // pre-double (see m31_mul_dbl); entries of layers below jlo are never read
-#pragma unroll
-    for (int q = 0; q < 15; ++q) tw[q] = tw[q] << 1;
     const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
     if (b == 0) {
       // the 16 words of a thread are contiguous: 4 x 128-bit shared accesses
@@ -224,9 +235,14 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
       u32* __restrict__ dcol = p.dst + (size_t)(col0 + c) * p.dst_stride;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const u32 s = (tid + it * NT) * 4;
-        const size_t g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
-        uint4 v = *reinterpret_cast<const uint4*>(sm + (c << T) + swz2(s));
+        u32 ph; size_t g;
+        if (AFFINE) { ph = phys0 + it * NT * 4; g = g0 + it * gstep; }
+        else {
+          const u32 s = (tid + it * NT) * 4;
+          ph = swz2(s);
+          g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+        }
+        uint4 v = *reinterpret_cast<const uint4*>(sm + (c << T) + ph);
         if (p.apply_scale) { const u32 sc2 = p.scale << 1; v.x = m31_mul_dbl(v.x, sc2); v.y = m31_mul_dbl(v.y, sc2); v.z = m31_mul_dbl(v.z, sc2); v.w = m31_mul_dbl(v.w, sc2); }
         *reinterpret_cast<uint4*>(dcol + g) = v;
       }
@@ -476,7 +492,8 @@ static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* s
   p.tw_len = 1u << ctx->tw.half_log;
   const u32 *cf = nullptr, *ci = nullptr;
   NB_TRY(circle_tables(ctx, n, &cf, &ci));
-  p.ctw = INV ? ci : cf;
+  p.ctw2 = INV ? ci : cf;
+  p.tw2 = INV ? ctx->tw.d_itw2 : ctx->tw.d_tw2;
   p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
   p.cb = pl.T >= 13 ? 2 : 4;
   if (p.cb > n_cols) p.cb = (u32)n_cols;

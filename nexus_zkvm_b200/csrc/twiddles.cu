@@ -3,7 +3,8 @@
 // Layout (identical to stwo's TwiddleTree buffer so every smaller domain's twiddles are suffix slices):
 //   for l in 0..k: 2^(k-1-l) x-coordinates of the first half of (root doubled l times), bit-reversed; then one pad word 1.
 // Generated on the device: each thread turns its point index into a point with <= 31 group additions from a
-// constant-memory table of generator doublings, and inverts it by Fermat.
+// constant-memory table of generator doublings, and inverts it by Fermat.  Doubled copies (2t, 2/t) feed the FFT's
+// multiply (stwo's SIMD backend keeps `twiddle_dbl` for the same reason).
 #include "common.cuh"
 #include "circle_host.h"
 
@@ -19,7 +20,7 @@ __device__ __forceinline__ cpoint dev_index_to_point(u32 idx) {
   return r;
 }
 
-__global__ void twiddle_bank_kernel(u32* __restrict__ tw, u32* __restrict__ itw, u32 k) {
+__global__ void twiddle_bank_kernel(u32* __restrict__ tw, u32* __restrict__ itw, u32* __restrict__ tw2, u32* __restrict__ itw2, u32 k) {
   u32 e = blockIdx.x * blockDim.x + threadIdx.x;
   u32 len = 1u << k;
   if (e >= len) return;
@@ -41,15 +42,19 @@ __global__ void twiddle_bank_kernel(u32* __restrict__ tw, u32* __restrict__ itw,
     u32 idx = (init + (u32)(((u64)step * jr) & 0x7fffffffu)) & 0x7fffffffu;
     x = dev_index_to_point(idx).x;
   }
-  tw[e] = x;
-  itw[e] = m31_inv(x);
+  u32 xi = m31_inv(x);
+  tw[e] = x; itw[e] = xi; tw2[e] = x << 1; itw2[e] = xi << 1;
 }
 
 nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log) {
   NB_ARG(ctx, max_domain_log >= 1 && max_domain_log <= 30, "twiddles: domain log out of range");
   u32 k = max_domain_log - 1;
   if (ctx->tw.d_tw && ctx->tw.half_log >= k) return NB200_OK;
-  if (ctx->tw.d_tw) { cudaFree(ctx->tw.d_tw); cudaFree(ctx->tw.d_itw); ctx->tw = TwiddleBank(); }
+  if (ctx->tw.d_tw) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->tw.d_tw); cudaFree(ctx->tw.d_itw); cudaFree(ctx->tw.d_tw2); cudaFree(ctx->tw.d_itw2);
+    ctx->tw = TwiddleBank();
+  }
   static bool table_uploaded[64] = {false};
   if (!table_uploaded[ctx->device & 63]) {
     NB_CUDA(ctx, cudaMemcpyToSymbol(c_gen_pow2, gen_table().pow2, sizeof(cpoint) * 31));
@@ -58,9 +63,11 @@ nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log) {
   size_t len = (size_t)1 << k;
   NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_tw, len * 4));
   NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_itw, len * 4));
+  NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_tw2, len * 4));
+  NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_itw2, len * 4));
   ctx->tw.half_log = k;
   u32 threads = 256, blocks = (u32)((len + threads - 1) / threads);
-  twiddle_bank_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tw.d_tw, ctx->tw.d_itw, k);
+  twiddle_bank_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tw.d_tw, ctx->tw.d_itw, ctx->tw.d_tw2, ctx->tw.d_itw2, k);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
