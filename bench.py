@@ -278,10 +278,21 @@ def main():
             torch.cuda.synchronize()
             h2d = sum(h.numel() * 4 for h in host)
 
+            host_np = [h.numpy().view(np.uint32) for h in host]
+
             def e2e_step():
-                for h, t in zip(host, evals_t):
-                    t.copy_(h, non_blocking=True)
-                return step()  # roots come back to the host inside commit (32 B D2H per tree)
+                # the public host-column entry point: chunked H2D on a side stream overlapped with the transforms of the
+                # previous chunk, then Merkle; the 32-byte root comes back to the host inside the call (D2H per tree)
+                roots_ = []
+                for t in range(len(tree_cols)):
+                    if state["trees"][t] is not None:
+                        state["trees"][t].free()
+                    _, _, _, tree = ctx.commit_host([host_np[t]], args.log_blowup, evals=[evals[t]],
+                                                    coeffs=[state["coeffs"][t]], ldes=[state["ldes"][t]])
+                    state["trees"][t] = tree
+                    roots_.append(tree.root)
+                assert roots_ == roots, "e2e roots differ from the device-resident run"
+                return roots_
 
             e2e_step()
             barrier()
@@ -348,7 +359,8 @@ def run_full_prove(ctx, args, torch, reps=2):
     from nexus_zkvm_b200 import machine as M
     from nexus_zkvm_b200.prover import CudaBackend
     m = M.AddMachine(log_size=args.log_rows, n_lanes=args.prove_lanes)
-    cols, mult = m.fill_main_trace(seed=1)
+    # the host fills the trace straight into pinned memory handed out by the library (nb200_host_alloc)
+    cols, mult = m.fill_main_trace(seed=1, out=ctx.host_alloc(m.n_main_columns(), args.log_rows))
     be = CudaBackend(ctx)
     times = []
     for _ in range(reps + 1):

@@ -118,6 +118,17 @@ nb200_status nb200_commit_evals(nb200_ctx*, const nb200_cols* const* eval_batche
                                 nb200_cols** coeffs_io /* n_batches */, nb200_cols** lde_io /* n_batches */,
                                 nb200_tree** tree_out, uint8_t root[32]);
 
+/* ---- host-column entry points: the reference hands over host `Vec<BaseColumn>`s (trace_builder.rs:156-164) ---- */
+/* pinned host memory for trace columns (H2D at link speed, and real copy/compute overlap below) */
+nb200_status nb200_host_alloc(size_t bytes, void** out);
+void nb200_host_free(void*);
+/* nb200_commit_evals from HOST columns: batch b is n_cols[b] x 2^log_sizes[b] words at host_batches[b].  Column chunks
+ * are copied on a side stream while the previous chunk is transformed; with coset_order != 0 the device also applies
+ * finalize_columns.  evals_io / coeffs_io / lde_io as in nb200_commit_evals (NULL entries are allocated). */
+nb200_status nb200_commit_host(nb200_ctx*, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes,
+                               size_t n_batches, int coset_order, uint32_t log_blowup, nb200_cols** evals_io, nb200_cols** coeffs_io,
+                               nb200_cols** lde_io, nb200_tree** tree_out, uint8_t root[32]);
+
 /* ---- Blake2sChannel (stwo core/channel/blake2s.rs; used at machine.rs:197-206,240,262) --------------- */
 /* The Fiat-Shamir transcript is sequential host work; it is part of the library so that the Rust shim and the
  * coarse nb200_prove share one implementation.  ctx may be NULL (defaults for the flavour switches). */
@@ -150,6 +161,10 @@ void nb200_scheme_free(nb200_scheme*);
 /* tree_builder.extend_evals(batches...); tree_builder.commit(channel)  (machine.rs:208-263): interpolate, LDE,
  * Merkle, mix_root.  The evaluation batches are only read. */
 nb200_status nb200_scheme_commit(nb200_scheme*, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel*, uint8_t root[32]);
+/* the same from HOST columns (pipelined H2D, optional finalize_columns on the device); evals_out[b] receives the device
+ * evaluation batches (owned by the caller; nb200_gen_interaction_trace reads them) */
+nb200_status nb200_scheme_commit_host(nb200_scheme*, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes,
+                                      size_t n_batches, int coset_order, nb200_channel*, uint8_t root[32], nb200_cols** evals_out);
 /* generate_interaction_trace for one component (machine.rs:242-260; LogupTraceGenerator semantics) from the committed
  * preprocessed (tree0) and main (tree1) evaluation batches; params = n_params QM31 (lookup elements).
  * Out: a new batch of 4 * n_logup_columns columns and the component's claimed sum.  SURVEY §8 row f2. */

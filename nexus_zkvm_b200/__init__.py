@@ -70,6 +70,7 @@ class Context:
         st = lib().nb200_ctx_create(C.c_int(device), C.byref(self._h))
         if st != 0:
             raise Nb200Error(f"nb200_ctx_create failed ({st}): {lib().nb200_last_error(None).decode()}")
+        self._pinned = []
         if stream is not None:
             self._chk(lib().nb200_ctx_set_stream(self._h, C.c_void_p(stream)))
 
@@ -81,6 +82,9 @@ class Context:
         if self._h:
             lib().nb200_ctx_destroy(self._h)
             self._h = C.c_void_p()
+            for p, _buf in self._pinned:
+                lib().nb200_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -161,6 +165,40 @@ class Context:
         root = (C.c_uint8 * 32)()
         self._chk(lib().nb200_merkle_commit(self._h, arr, C.c_size_t(len(batches)), C.byref(t), root))
         return MerkleTree(self, t, bytes(root), list(batches))
+
+    def host_alloc(self, n_cols, log_size):
+        """Pinned host memory for a block of trace columns, as an (n_cols, 2^log_size) uint32 numpy array."""
+        n = n_cols << log_size
+        p = C.c_void_p()
+        st = lib().nb200_host_alloc(C.c_size_t(4 * max(n, 1)), C.byref(p))
+        if st:
+            raise Nb200Error(f"nb200_host_alloc failed ({st})")
+        buf = (C.c_uint32 * max(n, 1)).from_address(p.value)
+        arr = np.ctypeslib.as_array(buf)[:n].reshape(n_cols, 1 << log_size)
+        self._pinned.append((p, buf))
+        return arr
+
+    def commit_host(self, host_batches, log_blowup, coset_order=False, evals=None, coeffs=None, ldes=None):
+        """Commit from HOST batches (2-D uint32 arrays; pinned for copy/compute overlap): returns (evals, coeffs, ldes, tree)."""
+        n = len(host_batches)
+        hb = [np.ascontiguousarray(b, dtype=np.uint32) for b in host_batches]
+        ptrs = (u32p * n)(*[b.ctypes.data_as(u32p) for b in hb])
+        ncols = (C.c_size_t * n)(*[b.shape[0] for b in hb])
+        logs = (C.c_uint32 * n)(*[int(b.shape[1]).bit_length() - 1 for b in hb])
+        ev = (C.c_void_p * n)(*([b._h for b in evals] if evals else [None] * n))
+        co = (C.c_void_p * n)(*([b._h for b in coeffs] if coeffs else [None] * n))
+        ld = (C.c_void_p * n)(*([b._h for b in ldes] if ldes else [None] * n))
+        t = C.c_void_p()
+        root = (C.c_uint8 * 32)()
+        self._chk(lib().nb200_commit_host(self._h, ptrs, ncols, logs, C.c_size_t(n), C.c_int(1 if coset_order else 0), C.c_uint32(log_blowup),
+                                          ev, co, ld, C.byref(t), root))
+        if evals is None:
+            evals = [Columns(self, C.c_void_p(ev[i])) for i in range(n)]
+        if coeffs is None:
+            coeffs = [Columns(self, C.c_void_p(co[i])) for i in range(n)]
+        if ldes is None:
+            ldes = [Columns(self, C.c_void_p(ld[i])) for i in range(n)]
+        return evals, coeffs, ldes, MerkleTree(self, t, bytes(root), ldes)
 
     def commit_evals(self, eval_batches, log_blowup, coeffs=None, ldes=None):
         """TreeBuilder.extend_evals(evals) + commit(): returns (coeff_batches, lde_batches, tree).

@@ -66,6 +66,10 @@ void nb200_ctx_destroy(nb200_ctx* ctx) {
   if (ctx->tw.d_tw2) cudaFree(ctx->tw.d_tw2);
   if (ctx->tw.d_itw2) cudaFree(ctx->tw.d_itw2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->copy_stream) {
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->copy_ev[i]); cudaEventDestroy(ctx->done_ev[i]); }
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -272,6 +276,83 @@ nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t
   if (left) { b.update(left, 32); b.update(right, 32); }
   for (size_t i = 0; i < n_values; ++i) { uint8_t le[4] = {(uint8_t)values[i], (uint8_t)(values[i] >> 8), (uint8_t)(values[i] >> 16), (uint8_t)(values[i] >> 24)}; b.update(le, 4); }
   b.finalize(out);
+  return NB200_OK;
+}
+
+}  // extern "C" (reopened below)
+
+namespace nb {
+nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde) {
+  if (n_cols == 0) return NB200_OK;
+  if (!ctx->copy_stream) {
+    NB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      NB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+      NB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->done_ev[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t len = (size_t)1 << log_size, lde_len = len << log_blowup;
+  // ~256 MiB chunks, multiples of 4 columns (the FFT kernels batch 4 columns per CTA)
+  size_t chunk = std::max<size_t>(4, ((size_t)64 << 20) / len);
+  chunk = (chunk + 3) & ~(size_t)3;
+  if (chunk > n_cols) chunk = n_cols;
+  u32* tmp[2] = {nullptr, nullptr};
+  if (coset_order) for (int i = 0; i < 2; ++i) NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp[i], chunk * len * 4));
+  // the copy stream must not overtake work already queued on the compute stream that still reads the targets
+  NB_CUDA(ctx, cudaEventRecord(ctx->done_ev[0], ctx->stream));
+  NB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[0], 0));
+  nb200_status st = NB200_OK;
+  size_t k = 0;
+  for (size_t c0 = 0; c0 < n_cols && st == NB200_OK; c0 += chunk, ++k) {
+    const size_t nc = std::min(chunk, n_cols - c0);
+    const int slot = (int)(k & 1);
+    u32* dst = coset_order ? tmp[slot] : d_evals + c0 * len;
+    if (coset_order && k >= 2) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot], 0));  // tmp[slot] consumed?
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, host + c0 * len, nc * len * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
+    NB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
+    if (coset_order) {
+      st = reorder_coset_to_bitrev(ctx, tmp[slot], d_evals + c0 * len, nc, log_size);
+      if (st == NB200_OK) NB_CUDA(ctx, cudaEventRecord(ctx->done_ev[slot], ctx->stream));
+    }
+    if (st == NB200_OK) st = fft_interpolate(ctx, d_evals + c0 * len, d_coeffs + c0 * len, nc, log_size);
+    if (st == NB200_OK) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_lde + c0 * lde_len, log_size + log_blowup, nc);
+  }
+  if (coset_order) { dfree(ctx, tmp[0]); dfree(ctx, tmp[1]); }
+  return st;
+}
+}  // namespace nb
+
+extern "C" {
+
+nb200_status nb200_host_alloc(size_t bytes, void** out) {
+  if (!out) return NB200_ERR_ARG;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+  return e == cudaSuccess ? NB200_OK : NB200_ERR_OOM;
+}
+void nb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes, size_t n_batches,
+                               int coset_order, uint32_t log_blowup, nb200_cols** evals_io, nb200_cols** coeffs_io, nb200_cols** lde_io,
+                               nb200_tree** tree_out, uint8_t root[32]) {
+  if (!ctx || !host_batches || !evals_io || !coeffs_io || !lde_io || !tree_out) return NB200_ERR_ARG;
+  u32 max_log = 0;
+  for (size_t b = 0; b < n_batches; ++b) max_log = std::max(max_log, log_sizes[b] + log_blowup);
+  if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
+  std::vector<ColRef> cols;
+  for (size_t b = 0; b < n_batches; ++b) {
+    if (!evals_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &evals_io[b]));
+    if (!coeffs_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &coeffs_io[b]));
+    if (!lde_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + log_blowup, &lde_io[b]));
+    NB_ARG(ctx, evals_io[b]->n_cols == n_cols[b] && evals_io[b]->log_size == log_sizes[b] && coeffs_io[b]->n_cols == n_cols[b] &&
+                    coeffs_io[b]->log_size == log_sizes[b] && lde_io[b]->n_cols == n_cols[b] && lde_io[b]->log_size == log_sizes[b] + log_blowup,
+           "commit_host: batch shapes");
+    NB_TRY(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d));
+    for (size_t c = 0; c < n_cols[b]; ++c) cols.push_back(ColRef{lde_io[b]->col(c), lde_io[b]->log_size});
+  }
+  NB_TRY(merkle_commit(ctx, cols, tree_out));
+  if (root) memcpy(root, (*tree_out)->root, 32);
   return NB200_OK;
 }
 

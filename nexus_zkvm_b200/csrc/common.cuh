@@ -31,6 +31,8 @@ struct nb200_ctx {
   uint64_t launches = 0;
   int trace = 0;          // NB200_TRACE=1: per-stage wall clock (after a stream sync) on stderr
   double trace_t0 = 0;
+  cudaStream_t copy_stream = nullptr;  // H2D side stream of the pipelined host-column path
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr}, done_ev[2] = {nullptr, nullptr};
   // scratch for small device->host transfers
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
@@ -105,6 +107,10 @@ nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_
 // Circle FFT: coefficients (src, log src_log) zero-extended to dst (log dst_log); src may equal dst if logs match
 nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols);
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
+// Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)
+// overlaps the transforms of chunk k.  `host` is n_cols x 2^log_size words (pinned memory for real overlap).
+nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde);
 
 struct ColRef { const u32* d; u32 log_size; };
 nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out);

@@ -96,6 +96,35 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
   return NB200_OK;
 }
 
+// The same, from HOST columns (the reference hands over host `Vec<BaseColumn>`s, trace_builder.rs:156-164): upload,
+// finalize_columns on the device when `coset_order`, transforms — pipelined chunk by chunk — then Merkle + mix_root.
+nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const size_t* n_cols, const u32* log_sizes, size_t n, int coset_order,
+                                HostChannel& ch, uint8_t root[32], nb200_cols** evals_out) {
+  nb200_ctx* ctx = s->ctx;
+  u32 max_log = 0;
+  for (size_t b = 0; b < n; ++b) max_log = std::max(max_log, log_sizes[b] + s->log_blowup);
+  if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
+  trace_mark(ctx, nullptr);
+  SchemeTree t;
+  for (size_t b = 0; b < n; ++b) {
+    nb200_cols *ev = nullptr, *co = nullptr, *lde = nullptr;
+    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &ev));
+    evals_out[b] = ev;
+    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &co));
+    t.coeffs.push_back(co);
+    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + s->log_blowup, &lde));
+    t.ldes.push_back(lde);
+    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d));
+  }
+  trace_mark(ctx, "commit(host): h2d+ifft+lde");
+  nb200_status st = finish_tree(ctx, t, ch);
+  if (st != NB200_OK) { free_tree(ctx, t); return st; }
+  trace_mark(ctx, "commit: merkle");
+  if (root) memcpy(root, t.merkle->root, 32);
+  s->trees.push_back(std::move(t));
+  return NB200_OK;
+}
+
 // ---- host-side point-mode interpreter (PointEvaluator) for the prover's sanity check ----
 static qm31 from_partial_evals(const qm31 v[4]) {
   qm31 I = qm31_make(0, 1, 0, 0), U = qm31_make(0, 0, 1, 0), IU = qm31_make(0, 0, 0, 1);
@@ -648,6 +677,11 @@ void nb200_scheme_free(nb200_scheme* s) {
 nb200_status nb200_scheme_commit(nb200_scheme* s, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel* channel, uint8_t root[32]) {
   if (!s || !channel) return NB200_ERR_ARG;
   return scheme_commit_evals(s, eval_batches, n_batches, channel->ch, root);
+}
+nb200_status nb200_scheme_commit_host(nb200_scheme* s, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes, size_t n_batches,
+                                      int coset_order, nb200_channel* channel, uint8_t root[32], nb200_cols** evals_out) {
+  if (!s || !channel || !host_batches || !evals_out) return NB200_ERR_ARG;
+  return scheme_commit_host(s, host_batches, n_cols, log_sizes, n_batches, coset_order, channel->ch, root, evals_out);
 }
 nb200_status nb200_gen_interaction_trace(nb200_ctx* ctx, const nb200_air* air, uint32_t component, const nb200_cols* const* tree0, size_t n0,
                                          const nb200_cols* const* tree1, size_t n1, const uint32_t* params, size_t n_params,

@@ -75,11 +75,29 @@ class AddMachine:
         cols[self.air.preprocessed_ids["Range256Values"]] = np.arange(256, dtype=np.uint32)
         return cols
 
-    def fill_main_trace(self, seed=0, n_padding=0):
-        """ADD chain: every lane adds two pseudo-random 32-bit words per row."""
+    def n_main_columns(self):
+        """Columns of the main component in tree 1 (the multiplicity column of the table component comes after them)."""
+        return 2 + 16 * self.n_lanes
+
+    def fill_main_trace(self, seed=0, n_padding=0, out=None):
+        """ADD chain: every lane adds two pseudo-random 32-bit words per row.  With `out` (an (n_main_columns, 2^log_size)
+        uint32 array, e.g. pinned memory from Context.host_alloc) the columns are written in place and `out` is returned."""
         n = 1 << self.log_size
         rng = np.random.default_rng(seed)
-        cols = []
+
+        class _Sink(list):
+            def append(self_inner, col):
+                if out is not None:
+                    out[len(self_inner)] = col
+                    col = out[len(self_inner)]
+                list.append(self_inner, col)
+
+            def __iadd__(self_inner, more):
+                for c in more:
+                    self_inner.append(c)
+                return self_inner
+
+        cols = _Sink()
         cols.append((4 * np.arange(n, dtype=np.uint64) % P).astype(np.uint32))  # pc
         pad = np.zeros(n, np.uint32)
         if n_padding:
@@ -103,7 +121,7 @@ class AddMachine:
                 hist += np.bincount(x, minlength=256)
         assert len(cols) == self.air.n_columns()[1] - 1
         mult = (hist % P).astype(np.uint32)
-        return cols, mult
+        return (out if out is not None else list(cols)), mult
 
     def column_log_sizes(self):
         return self.air.column_log_sizes()
@@ -123,7 +141,8 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
     # tree 0: preprocessed (machine.rs:208-228)
     roots = [prover.commit(machine.preprocessed_columns(), ch, coset_order=True)]
     # tree 1: main trace + extension main columns (machine.rs:230-237)
-    roots.append(prover.commit(list(main_cols) + [mult], ch, coset_order=True))
+    main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)  # a 2-D block or a list of columns
+    roots.append(prover.commit(main_part + [mult], ch, coset_order=True))
     # lookup elements (machine.rs:239-240)
     params = [(0, 0, 0, 0)] * air.n_params
     machine.range256.draw(ch, params)

@@ -110,8 +110,43 @@ class CommitmentSchemeProver:
         self.tree_evals.append(list(batches))
         return bytes(root)
 
+    @staticmethod
+    def _host_batches(cols):
+        """Normalise `cols` (1-D columns and/or 2-D blocks of columns, commitment order) into contiguous 2-D host batches.
+        2-D blocks are used as they are (no copy) — fill the trace straight into `ctx.host_alloc` memory for H2D at link speed."""
+        out, run = [], []
+
+        def flush():
+            if run:
+                out.append(np.stack(run))
+                run.clear()
+
+        for c in cols:
+            a = np.asarray(c)
+            if a.ndim == 2:
+                flush()
+                out.append(np.ascontiguousarray(a, dtype=np.uint32))
+            else:
+                a = np.ascontiguousarray(a, dtype=np.uint32)
+                if run and run[0].size != a.size:
+                    flush()
+                run.append(a)
+        flush()
+        return out
+
     def commit(self, cols, ch, coset_order=False):
-        return self.commit_batches(self._batches_from_host(cols, coset_order), ch)
+        """tree_builder.extend_evals(host columns); commit(channel) — pipelined H2D + transforms (nb200_scheme_commit_host)."""
+        hb = self._host_batches(cols)
+        n = len(hb)
+        ptrs = (u32p * n)(*[b.ctypes.data_as(u32p) for b in hb])
+        ncols = (C.c_size_t * n)(*[b.shape[0] for b in hb])
+        logs = (C.c_uint32 * n)(*[int(b.shape[1]).bit_length() - 1 for b in hb])
+        evals = (C.c_void_p * n)()
+        root = (C.c_uint8 * 32)()
+        self.ctx._chk(lib().nb200_scheme_commit_host(self._h, ptrs, ncols, logs, C.c_size_t(n), C.c_int(1 if coset_order else 0), ch._h, root, evals))
+        self.ctx.sync()  # the host batches may be released by the caller after this returns
+        self.tree_evals.append([Columns(self.ctx, C.c_void_p(evals[i])) for i in range(n)])
+        return bytes(root)
 
     def gen_interaction(self, comp, log_size, n_logup_cols, params):
         p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))

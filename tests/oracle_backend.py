@@ -11,7 +11,11 @@ class _OracleProver:
         self.config = config
 
     def commit(self, cols, ch, coset_order=False):
-        cols = [np.ascontiguousarray(c, dtype=np.uint32) for c in cols]
+        flat = []
+        for c in cols:  # 2-D blocks of columns are accepted like the product backend does
+            a = np.asarray(c)
+            flat += list(a) if a.ndim == 2 else [a]
+        cols = [np.ascontiguousarray(c, dtype=np.uint32) for c in flat]
         if coset_order:
             cols = [orc.finalize_column(c) for c in cols]
         return self.p.commit(cols, ch, self.config["log_blowup"])

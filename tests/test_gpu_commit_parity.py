@@ -153,3 +153,22 @@ def test_commit_evals_matches_oracle_pipeline(ctx, logs):
         assert np.array_equal(lde.download(), ol)
         flat += list(ol)
     assert tree.root == orc.merkle_commit(flat)
+
+
+@pytest.mark.parametrize("coset_order", [False, True])
+def test_commit_host_pipelined_matches_oracle(ctx, coset_order):
+    # host columns in pinned memory -> chunked H2D overlapped with the transforms (2 chunks at this size) -> Merkle
+    rng = np.random.default_rng(99)
+    log, n_cols = 18, 300
+    host = ctx.host_alloc(n_cols, log)
+    host[:] = rng.integers(0, P, (n_cols, 1 << log), dtype=np.uint32)
+    small = rng.integers(0, P, (3, 1 << 6), dtype=np.uint32)
+    evals, coeffs, ldes, tree = ctx.commit_host([host, small], 1, coset_order=coset_order)
+    ref = [np.stack([orc.finalize_column(c) for c in b]) if coset_order else b for b in (host, small)]
+    flat = []
+    for r, ev, lde in zip(ref, evals, ldes):
+        assert np.array_equal(ev.download(), r)
+        _, ol = orc.interpolate_evaluate_batch(r, 1)
+        assert np.array_equal(lde.download(), ol)
+        flat += list(ol)
+    assert tree.root == orc.merkle_commit(flat)

@@ -23,10 +23,11 @@ def main():
     t0 = time.perf_counter()
     m = M.AddMachine(log_size=a.log_rows, n_lanes=a.lanes)
     t1 = time.perf_counter()
-    cols, mult = m.fill_main_trace(seed=1)
+    ctx = nb.Context(0)
+    cols, mult = m.fill_main_trace(seed=1, out=ctx.host_alloc(m.n_main_columns(), a.log_rows))
     t2 = time.perf_counter()
     print(f"[host] build AIR {1e3 * (t1 - t0):.1f} ms, fill trace {1e3 * (t2 - t1):.1f} ms, bytecode {m.words.size} words", file=sys.stderr)
-    be = CudaBackend(nb.Context(0))
+    be = CudaBackend(ctx)
     for r in range(a.reps):
         print(f"---- rep {r}", file=sys.stderr)
         t = time.perf_counter()
