@@ -281,59 +281,75 @@ class ComponentBuilder:
 
     def _emit(self, sinks):
         """Emit code for `sinks` = [(sink_op, node, node|None)] in declaration order: before each sink, the not yet
-        computed part of its expression DAG (post-order), then the sink itself.  Registers are reused as soon as a
-        value's last consumer has been emitted (the interpreters read all operands before writing the result)."""
+        computed part of its expression DAG (post-order), then the sink itself.  Leaves (mask loads, constants,
+        parameters) are rematerialised per sink instead of being kept alive — a reload is one instruction, a long live
+        range is a virtual register held for thousands of instructions (the interpreter keeps registers in shared
+        memory, so the register count sets the occupancy).  Registers are reused as soon as an instance's last
+        consumer has been emitted (the interpreters read all operands before writing the result)."""
+        LEAVES = ("mask", "maske", "const", "param")
         seq = []          # ("n", node) | ("s", sink index)
         done = set()
         for idx, s in enumerate(sinks):
+            fresh = set()  # leaves already emitted for this sink
             for root in s[1:]:
-                if root is None or root in done:
+                if root is None or root in done or root in fresh:
                     continue
                 stack = [(root, False)]
                 while stack:
                     n, expanded = stack.pop()
-                    if n in done:
+                    if n in done or n in fresh:
                         continue
                     if expanded:
-                        done.add(n)
+                        (fresh if self.nodes[n][0] in LEAVES else done).add(n)
                         seq.append(("n", n))
                         continue
                     stack.append((n, True))
                     for x in reversed(self._operands(n)):
-                        if x not in done:
+                        if x not in done and x not in fresh:
                             stack.append((x, False))
             seq.append(("s", idx))
-        last_use = {}
-        for pos, (kind, v) in enumerate(seq):
-            for x in (self._operands(v) if kind == "n" else [y for y in sinks[v][1:] if y is not None]):
-                last_use[x] = pos
-        reg, out = {}, []
+        # a shared non-leaf value computed under an earlier sink may read a leaf that is re-emitted later: that is fine,
+        # each emission is its own instance.  Instance liveness: backward scan.
+        last = {}          # node -> position of the last use of the instance currently being scanned
+        inst_last = {}     # definition position -> last use position (or None)
+        for pos in range(len(seq) - 1, -1, -1):
+            kind, v = seq[pos]
+            if kind == "n":
+                inst_last[pos] = last.pop(v, None)
+                for x in self._operands(v):
+                    last.setdefault(x, pos)
+            else:
+                for x in sinks[v][1:]:
+                    if x is not None:
+                        last.setdefault(x, pos)
+        free_at = {}
+        for dpos, lpos in inst_last.items():
+            if lpos is not None:
+                free_at.setdefault(lpos, []).append(dpos)
+        reg, reg_of_def, out = {}, {}, []
         free = {"B": [], "E": []}
         nreg = {"B": 0, "E": 0}
-
-        def release(x, pos):
-            if last_use.get(x) == pos:
-                free[self.nodes[x][3]].append(reg[x])
-
         for pos, (kind, v) in enumerate(seq):
             if kind == "s":
                 sop, n1, n2 = sinks[v]
                 out.append((sop, 0, reg[n1], reg[n2] if n2 is not None else 0))
-                for x in {y for y in (n1, n2) if y is not None}:
-                    release(x, pos)
+            else:
+                op, a, b, k = self.nodes[v]
+                ops = self._operands(v)
+                ra = reg[a] if ops else None
+                rb = reg[b] if len(ops) == 2 else None
+            # release every instance whose last use is this position (operands are read before the result is written)
+            for dpos in free_at.get(pos, []):
+                free[self.nodes[seq[dpos][1]][3]].append(reg_of_def[dpos])
+            if kind == "s":
                 continue
-            op, a, b, k = self.nodes[v]
-            ops = self._operands(v)
-            ra = reg[a] if ops else None
-            rb = reg[b] if len(ops) == 2 else None
-            for x in set(ops):
-                release(x, pos)
             if free[k]:
                 r = free[k].pop()
             else:
                 r = nreg[k]
                 nreg[k] += 1
             reg[v] = r
+            reg_of_def[pos] = r
             if op == "mask":
                 out.append((OP_LOADM, r, a, 0))
             elif op == "maske":
@@ -348,7 +364,7 @@ class ComponentBuilder:
                 out.append((self._OPS[("neg", k)], r, ra, 0))
             else:
                 out.append((self._OPS[(op, k)], r, ra, rb))
-            if v not in last_use:
+            if inst_last[pos] is None:
                 free[k].append(r)
         return out, nreg["B"], nreg["E"]
 
