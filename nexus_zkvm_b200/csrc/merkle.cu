@@ -19,7 +19,7 @@ namespace nb {
 
 template <int VARIANT>
 __global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restrict__ prev, const u32* const* __restrict__ cols,
-                                                            u32 n_cols, u32 log_size, uint4* __restrict__ out) {
+                                                            u32 n_cols, u32 log_size, uint4* __restrict__ out, const u32 one) {
   const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= ((size_t)1 << log_size)) return;
   u32 h[8];
@@ -39,16 +39,16 @@ __global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restri
     m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
     m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
     if (VARIANT == 0) {
-      b2s_compress(h, m, 0, 0, 0, 0);
+      b2s_compress_fma(h, m, 0, 0, 0, 0, one);
     } else {
       t = 64;
       bool last = (n_cols == 0);
-      b2s_compress(h, m, (u32)t, 0, last ? 0xFFFFFFFFu : 0u, 0);
+      b2s_compress_fma(h, m, (u32)t, 0, last ? 0xFFFFFFFFu : 0u, 0, one);
     }
   } else if (VARIANT == 1 && n_cols == 0) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) m[i] = 0;
-    b2s_compress(h, m, 0, 0, 0xFFFFFFFFu, 0);
+    b2s_compress_fma(h, m, 0, 0, 0xFFFFFFFFu, 0, one);
   }
   for (u32 c0 = 0; c0 < n_cols; c0 += 16) {
     if (c0 + 16 <= n_cols) {
@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restri
       for (int j = 0; j < 16; ++j) m[j] = (c0 + j < n_cols) ? __ldg(cols[c0 + j] + row) : 0u;
     }
     if (VARIANT == 0) {
-      b2s_compress(h, m, 0, 0, 0, 0);
+      b2s_compress_fma(h, m, 0, 0, 0, 0, one);
     } else {
       bool last = (c0 + 16 >= n_cols);
       t = last ? total_bytes : t + 64;
-      b2s_compress(h, m, (u32)t, (u32)(t >> 32), last ? 0xFFFFFFFFu : 0u, 0);
+      b2s_compress_fma(h, m, (u32)t, (u32)(t >> 32), last ? 0xFFFFFFFFu : 0u, 0, one);
     }
   }
   uint4* o = out + 2 * row;
@@ -108,9 +108,9 @@ nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, n
     u32 threads = 128;
     u32 blocks = (u32)((rows + threads - 1) / threads);
     if (ctx->merkle_hash == 0)
-      merkle_layer_kernel<0><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l]);
+      merkle_layer_kernel<0><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l], 1u);
     else
-      merkle_layer_kernel<1><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l]);
+      merkle_layer_kernel<1><<<blocks, threads, 0, ctx->stream>>>(prev, d_ptrs + first, n_here, (u32)l, (uint4*)tree->layer[l], 1u);
     ctx->launches += 1;
   }
   e = cudaGetLastError();
