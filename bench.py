@@ -265,7 +265,11 @@ def main():
                       "merkle_GBps_read": (4.0 * elems * (1 << args.log_blowup)) / (t_mrk * 1e-3) / 1e9,
                       "fft_Melems_per_s": (elems * (1 + (1 << args.log_blowup))) / ((t_ifft + t_fft) * 1e-3) / 1e6}
             roofline = {"bound": "hbm", "kernel": "fft_pass_kernel (Circle iFFT + LDE FFT, all passes)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / hbm_peak,
+                        # dram__bytes_read+write of the 4 FFT launches from profiles/ncu_fft_r01b_tile_kernel.txt (64-column
+                        # capture, 41.3 B per trace element), scaled to this step's element count
+                        "traffic": 41.3 * elems, "traffic_unit": "B per step (all FFT passes)", "algorithmic": fft_bytes,
+                        "peak_source": peak_src,
                         "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
                         "time_share": {"fft": (t_ifft + t_fft) / (t_ifft + t_fft + t_mrk), "merkle": t_mrk / (t_ifft + t_fft + t_mrk)}}
 
