@@ -127,6 +127,8 @@ def run_reference(args):
     tree_cols = [int(x) for x in args.cols.split(",")]
     total_cols = sum(tree_cols)
     sample = min(args.cpu_sample_cols, total_cols)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, max(2, sample // 8))
@@ -335,6 +337,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import pyoracle as orc
+            orc.set_num_threads(os.cpu_count() or 1)
             sample = min(args.cpu_sample_cols, total_cols)
             tcpu = cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample)
             cpu_baseline = {"value": n_rows / (tcpu * total_cols / sample), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",

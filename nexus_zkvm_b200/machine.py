@@ -9,7 +9,7 @@ a next-row constraint on a program counter (mask offset +1, like `Pc`, prover/sr
 constraints (range_bool.rs), one LogUp fraction per range-checked byte with one secure column per fraction
 (`finalize_logup`, components/mod.rs:52-54), and a second, small component (a 2^8 multiplicity table with a
 preprocessed column addressed by id, like prover/src/extensions/multiplicity.rs) so that trees hold mixed-size columns.
-With 21 lanes the column counts are 3 / 341 / 1012 — the reference's 27 / 347 / 1012.
+With 21 lanes the column counts are 3 / 339 / 1012 — the reference's 27 / 347 / 1012.
 
 `prove(backend, ...)` is written against a small backend protocol (channel / prover.commit / gen_interaction /
 commit_interaction / prove); the product backend is nexus_zkvm_b200.prover.CudaBackend, and the parity tests plug
@@ -24,7 +24,9 @@ P = (1 << 31) - 1
 
 
 class AddMachine:
-    def __init__(self, log_size, n_lanes=1, log_expand=2):
+    def __init__(self, log_size, n_lanes=1, log_expand=2, logup_in_pairs=False):
+        """logup_in_pairs: batch the fractions two per secure column (`finalize_logup_in_pairs`, the prover2 style —
+        /root/reference prover2/machine/src/lookups/logup_trace_builder.rs:88-101) instead of one per column (v1)."""
         assert log_size >= 8
         self.log_size, self.n_lanes, self.log_expand = log_size, n_lanes, log_expand
         air = A.Air()
@@ -54,7 +56,10 @@ class AddMachine:
         for (a, b, c, carry) in lanes:
             for x in a + b + c:
                 main.add_to_relation(self.range256, 1, [x])
-        main.finalize_logup()
+        if logup_in_pairs:
+            main.finalize_logup_in_pairs()
+        else:
+            main.finalize_logup()
         table = air.component(8, 1)
         val = table.get_preprocessed_column("Range256Values")
         mult = table.next_trace_mask()

@@ -77,3 +77,35 @@ def test_constraints_not_satisfied_is_reported(backend):
     cols[2 + 8][17] = (int(cols[2 + 8][17]) + 1) % 256
     with pytest.raises(nb.Nb200Error, match="status 5"):
         M.prove(m, backend, cols, mult)
+
+
+def test_paired_logup_matches_oracle(backend):
+    # prover2-style batching: two fractions per secure column (finalize_logup_in_pairs)
+    m = M.AddMachine(log_size=9, n_lanes=2, logup_in_pairs=True)
+    assert m.air.n_columns()[2] == 4 * 12 + 4
+    cols, mult = m.fill_main_trace(seed=21, n_padding=2)
+    g_proof, g_claimed, _ = M.prove(m, backend, cols, mult)
+    o_proof, o_claimed, o_aux = M.prove(m, OracleBackend(), cols, mult)
+    assert g_claimed == o_claimed and g_proof == o_proof
+    verify(m, g_proof, o_aux)
+
+
+@pytest.mark.parametrize("merkle_hash,draw_sep", [(1, 0), (0, 1), (1, 1)])
+def test_transcript_flavours_match_oracle(merkle_hash, draw_sep):
+    # the parity-risk switches change the proof bytes consistently on both sides
+    ctx = nb.Context(0)
+    ctx.set_flavor(merkle_hash=merkle_hash, draw_domain_sep=draw_sep)
+    orc.set_flavor(merkle_hash=merkle_hash, draw_domain_sep=draw_sep)
+    try:
+        m = M.AddMachine(log_size=8, n_lanes=1)
+        cols, mult = m.fill_main_trace(seed=31)
+        g_proof, _, _ = M.prove(m, CudaBackend(ctx), cols, mult)
+        o_proof, _, o_aux = M.prove(m, OracleBackend(), cols, mult)
+        assert g_proof == o_proof
+        verify(m, g_proof, o_aux)
+        orc.set_flavor()
+        d_proof, _, _ = M.prove(m, OracleBackend(), cols, mult)
+        assert d_proof != o_proof  # the switch really changes the transcript
+    finally:
+        orc.set_flavor()
+        ctx.close()

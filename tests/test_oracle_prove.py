@@ -60,3 +60,11 @@ def test_larger_trace_with_mixed_sizes():
     proof, claimed, aux = M.prove(m, OracleBackend(), cols, mult)
     assert M.verify_claimed_sums(claimed)
     verify(m, proof, aux)
+
+
+def test_paired_logup_proof_verifies():
+    m = M.AddMachine(log_size=8, n_lanes=2, logup_in_pairs=True)
+    cols, mult = m.fill_main_trace(seed=6)
+    proof, claimed, aux = M.prove(m, OracleBackend(), cols, mult)
+    assert M.verify_claimed_sums(claimed)
+    verify(m, proof, aux)
