@@ -251,154 +251,6 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
 }
 
 // =====================================================================================================
-// pipelined fast path: one CTA walks GPC groups of CB columns of ONE tile position.  The next group is staged with
-// cp.async (LDGSTS, no register staging) into the other half of a double buffer while the current group is being
-// transformed, so the global-memory phases of a CTA overlap its own ALU phases (ncu showed the ALU pipe idle ~30 % of
-// the time because the 3 resident CTAs of the plain kernel hit their load/store phases together); the twiddle loads of
-// a round are also shared by all groups of the CTA through L1.
-// =====================================================================================================
-__device__ __forceinline__ void cp_async16(u32 smem_addr, const void* gptr, bool valid) {
-  // 16-byte asynchronous copy global -> shared; src-size 0 zero-fills (zero extension of the coefficient vector)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gptr), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <bool INV, int T, int W, int CB, int GPC>
-__global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_pipe_kernel(const FftPass p) {
-  extern __shared__ __align__(16) u32 sm[];  // 2 buffers x CB columns x 2^T words
-  constexpr int L = T - W;
-  constexpr int NT = 1 << (T - 4);
-  constexpr int NFULL = L / 4, REM = L % 4, NROUNDS = NFULL + (REM ? 1 : 0);
-  constexpr bool AFFINE = (NT * 4 >= 512) && (W <= T - 2);
-  static_assert(AFFINE, "pipelined kernel is only instantiated for affine staging shapes");
-  const u32 lo = p.lo, n = p.n;
-  const u32 tid = threadIdx.x;
-  const u32 tile = blockIdx.x;
-  const u32 mid_bits = W ? lo - W : 0;
-  const u32 tile_mid = tile & ((1u << mid_bits) - 1u);
-  const u32 tile_hi = tile >> mid_bits;
-  const size_t gbase = ((size_t)tile_hi << (lo + L)) | ((size_t)tile_mid << W);
-  const u32 colbase = blockIdx.y * (CB * GPC);
-  const u32 ncols_cta = min((u32)(CB * GPC), p.n_cols - colbase);
-  const u32 ngroups = (ncols_cta + CB - 1) / CB;
-
-  const u32 s0 = tid * 4;
-  const u32 phys0 = swz2(s0);
-  const size_t g0 = W ? (gbase | ((size_t)(s0 >> W) << lo) | (s0 & ((1u << W) - 1u))) : (gbase | s0);
-  const size_t gstep = W ? ((size_t)((NT * 4) >> W) << lo) : (size_t)(NT * 4);
-  const u32 sm_u32 = (u32)__cvta_generic_to_shared(sm);
-
-  auto prefetch = [&](u32 grp, u32 buf) {
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      const u32 col = colbase + grp * CB + c;
-      if (col < p.n_cols) {
-        const u32* __restrict__ scol = p.src + (size_t)col * p.src_stride;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const size_t g = g0 + it * gstep;
-          const bool valid = g < p.src_len;
-          cp_async16(sm_u32 + 4u * (((buf * CB + c) << T) + phys0 + it * NT * 4), scol + (valid ? g : 0), valid);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-
-  prefetch(0, 0);
-  for (u32 grp = 0; grp < ngroups; ++grp) {
-    const u32 buf = grp & 1u;
-    if (grp + 1 < ngroups) { prefetch(grp + 1, buf ^ 1u); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncthreads();
-    u32* smb = sm + ((buf * CB) << T);
-    const u32 ncb = min((u32)CB, ncols_cta - grp * CB);
-
-#pragma unroll
-    for (int rr = 0; rr < NROUNDS; ++rr) {
-      const int ri = INV ? rr : NROUNDS - 1 - rr;
-      const int b = ri < NFULL ? W + 4 * ri : T - 4;
-      const int jlo = ri < NFULL ? 0 : 4 - REM;
-      const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
-      u32 tw[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= jlo) {
-          const u32 i = lo + b + j - W;
-          const u32 hbase = (tile_hi << (L - (b + j - W) - 1)) | (tau_hi << (3 - j));
-          const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw2 + hbase) : (p.tw2 + (p.tw_len - (1u << (n - i))) + hbase);
-          if (j == 0) {
-            uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c4 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
-            tw[0] = a.x; tw[1] = a.y; tw[2] = a.z; tw[3] = a.w; tw[4] = c4.x; tw[5] = c4.y; tw[6] = c4.z; tw[7] = c4.w;
-          } else if (j == 1) {
-            uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-            tw[8] = a.x; tw[9] = a.y; tw[10] = a.z; tw[11] = a.w;
-          } else if (j == 2) {
-            uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
-            tw[12] = a.x; tw[13] = a.y;
-          } else {
-            tw[14] = __ldg(src);
-          }
-        }
-      }
-      const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
-      if (b == 0) {
-        const u32 a0 = swz2(sbase), a1 = swz2(sbase | 4u), a2 = swz2(sbase | 8u), a3 = swz2(sbase | 12u);
-#pragma unroll
-        for (int c = 0; c < CB; ++c) {
-          if (c < (int)ncb) {
-            u32* smc = smb + (c << T);
-            u32 v[16];
-            uint4 q0 = *reinterpret_cast<uint4*>(smc + a0), q1 = *reinterpret_cast<uint4*>(smc + a1);
-            uint4 q2 = *reinterpret_cast<uint4*>(smc + a2), q3 = *reinterpret_cast<uint4*>(smc + a3);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-            v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w; v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
-            radix16<INV>(v, tw, jlo);
-            *reinterpret_cast<uint4*>(smc + a0) = make_uint4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<uint4*>(smc + a1) = make_uint4(v[4], v[5], v[6], v[7]);
-            *reinterpret_cast<uint4*>(smc + a2) = make_uint4(v[8], v[9], v[10], v[11]);
-            *reinterpret_cast<uint4*>(smc + a3) = make_uint4(v[12], v[13], v[14], v[15]);
-          }
-        }
-      } else {
-        u32 addr[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) addr[k] = swz2(sbase | ((u32)k << b));
-#pragma unroll
-        for (int c = 0; c < CB; ++c) {
-          if (c < (int)ncb) {
-            u32* smc = smb + (c << T);
-            u32 v[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = smc[addr[k]];
-            radix16<INV>(v, tw, jlo);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) smc[addr[k]] = v[k];
-          }
-        }
-      }
-      __syncthreads();
-    }
-
-    // stage out this group (the barrier that ended the last round makes the tile visible)
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      if (c < (int)ncb) {
-        u32* __restrict__ dcol = p.dst + (size_t)(colbase + grp * CB + c) * p.dst_stride;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          uint4 v = *reinterpret_cast<const uint4*>(smb + (c << T) + phys0 + it * NT * 4);
-          if (p.apply_scale) { const u32 sc2 = p.scale << 1; v.x = m31_mul_dbl(v.x, sc2); v.y = m31_mul_dbl(v.y, sc2); v.z = m31_mul_dbl(v.z, sc2); v.w = m31_mul_dbl(v.w, sc2); }
-          *reinterpret_cast<uint4*>(dcol + g0 + it * gstep) = v;
-        }
-      }
-    }
-    __syncthreads();  // the buffer is refilled by the prefetch issued in the next iteration
-  }
-}
-
-// =====================================================================================================
 // generic fallback (runtime tile shape)
 // =====================================================================================================
 __device__ __forceinline__ u32 swz(u32 s) { return s ^ ((s >> 4) & 31u); }
@@ -621,29 +473,9 @@ static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
   return NB200_OK;
 }
 
-template <bool INV, int T, int W, int CB, int GPC>
-static nb200_status launch_tile_pipe(nb200_ctx* ctx, const FftPass& p) {
-  constexpr int threads = 1 << (T - 4);
-  constexpr size_t smem = (size_t)2 * CB << (T + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_pipe_kernel<INV, T, W, CB, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB * GPC - 1) / (CB * GPC)));
-  fft_tile_pipe_kernel<INV, T, W, CB, GPC><<<grid, threads, smem, ctx->stream>>>(p);
-  NB_LAUNCH_CHECK(ctx);
-  return NB200_OK;
-}
-
 // returns true if a specialised kernel exists for (T, W)
 template <bool INV>
 static bool launch_fast(nb200_ctx* ctx, const FftPass& p, nb200_status* st) {
-  if (p.n_cols >= 8) {  // enough columns per tile position to keep the double buffer busy
-#define NB_PIPE(TT, WW, CBB) if (p.T == TT && p.W == WW) { *st = launch_tile_pipe<INV, TT, WW, CBB, 8>(ctx, p); return true; }
-    NB_PIPE(12, 0, 2) NB_PIPE(13, 0, 1) NB_PIPE(12, 4, 2) NB_PIPE(12, 5, 2) NB_PIPE(12, 6, 2) NB_PIPE(12, 7, 2) NB_PIPE(12, 8, 2) NB_PIPE(13, 4, 1)
-#undef NB_PIPE
-  }
 #define NB_CASE(TT, WW, CBB) if (p.T == TT && p.W == WW) { *st = launch_tile<INV, TT, WW, CBB>(ctx, p); return true; }
   NB_CASE(9, 0, 4) NB_CASE(10, 0, 4) NB_CASE(11, 0, 4) NB_CASE(12, 0, 4) NB_CASE(13, 0, 2)
   NB_CASE(12, 4, 4) NB_CASE(12, 5, 4) NB_CASE(12, 6, 4) NB_CASE(12, 7, 4) NB_CASE(12, 8, 4) NB_CASE(13, 4, 2)

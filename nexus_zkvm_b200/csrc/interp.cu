@@ -9,6 +9,7 @@
 // memory laid out [register][thread] so every access is conflict-free; column reads are coalesced.
 #include "common.cuh"
 #include "air.h"
+#include "jit.h"
 #include "circle_host.h"
 
 namespace nb {
@@ -289,7 +290,7 @@ static nb200_status launch_interp(nb200_ctx* ctx, InterpArgs& a, u32 domain_log)
 // Evaluate the component's constraints on its evaluation domain and accumulate  sum_k coeff_k * c_k / vanishing  into acc.
 // mask_cols[m]: device pointer of mask m's column evaluated on CanonicCoset(eval_log).circle_domain().
 nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                             const std::vector<qm31>& coeffs, u32* const acc[4]) {
+                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk) {
   NB_ARG(ctx, mask_cols.size() == c.masks.size() && coeffs.size() == c.n_constraints, "constraint_eval: shape");
   const u32 elog = c.eval_log();
   // vanishing inverses: coset_vanishing(CanonicCoset(log_size).coset, eval_domain.at(i)) for i < 2^log_expand, bit-reversed
@@ -315,12 +316,23 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
   NB_CUDA(ctx, cudaMemcpyAsync(d_coeff, coeffs.data(), coeffs.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_dinv, dinv.size() * 4));
   NB_CUDA(ctx, cudaMemcpyAsync(d_dinv, dinv.data(), dinv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  InterpArgs a{};
-  a.prog = d_prog; a.n_instr = (u32)c.prog.size(); a.masks = d_masks; a.params = d_params;
-  a.nb = c.n_base_regs; a.ne = c.n_ext_regs; a.log_size = c.log_size; a.eval_log = elog;
-  a.coeff = d_coeff; a.dinv = d_dinv;
-  for (int k = 0; k < 4; ++k) a.acc[k] = acc[k];
-  nb200_status st = launch_interp<false>(ctx, a, elog);
+  nb200_status st;
+  if (jk && jk->kernel && jk->eval_log == elog && jk->log_size == c.log_size) {
+    // NVRTC-specialised kernel (jit.cu): same arithmetic, registers instead of the shared-memory register file
+    const u32** d_cols = nullptr;
+    NB_CUDA(ctx, dmalloc(ctx, (void**)&d_cols, mask_cols.size() * sizeof(u32*)));
+    NB_CUDA(ctx, cudaMemcpyAsync(d_cols, mask_cols.data(), mask_cols.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
+    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_coeff, d_dinv, acc);
+    cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, (void*)d_cols);
+  } else {
+    InterpArgs a{};
+    a.prog = d_prog; a.n_instr = (u32)c.prog.size(); a.masks = d_masks; a.params = d_params;
+    a.nb = c.n_base_regs; a.ne = c.n_ext_regs; a.log_size = c.log_size; a.eval_log = elog;
+    a.coeff = d_coeff; a.dinv = d_dinv;
+    for (int k = 0; k < 4; ++k) a.acc[k] = acc[k];
+    st = launch_interp<false>(ctx, a, elog);
+  }
   // host vectors were consumed by async copies: make sure they are done before the vectors die
   cudaStreamSynchronize(ctx->stream);
   dfree(ctx, d_prog); dfree(ctx, d_masks); dfree(ctx, d_coeff); dfree(ctx, d_dinv);

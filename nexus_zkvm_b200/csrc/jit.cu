@@ -1,0 +1,190 @@
+// Runtime specialisation of an AIR component's constraint program: the SSA bytecode (air.h) is translated to CUDA C,
+// compiled once per loaded AIR with NVRTC for sm_100a and launched instead of the bytecode interpreter
+// (interp.cu).  Same arithmetic, same accumulation order => bit-identical results; the point is that the virtual
+// registers become machine registers and the decode loop disappears (SURVEY.md §7.3-4 "NVRTC-specialised kernel").
+// Replaces, like the interpreter, FrameworkComponent::evaluate_constraint_quotients_on_domain reached from
+// stwo::prover::prove at /root/reference prover/src/machine.rs:286-290.
+//
+// libnvrtc is opened with dlopen at first use; if it is missing (or NB200_JIT=0) the interpreter kernels — also CUDA —
+// are used.  The generated function is cut into __noinline__ chunks of a few hundred statements: NVVM's optimiser is
+// super-linear in function size (27 s for one 4400-statement function vs 7 s chunked, measured).
+#include "pcs.h"
+#include "jit.h"
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sstream>
+#include <cstdlib>
+
+namespace nb {
+
+namespace {
+struct Nvrtc {
+  void* h = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  bool ok = false;
+};
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static bool tried = false;
+  if (tried) return n;
+  tried = true;
+  const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+  for (const char* nm : names) { n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (n.h) break; }
+  if (!n.h) return n;
+#define NB_SYM(f) n.f = (decltype(n.f))dlsym(n.h, "nvrtc" #f); if (!n.f) return n;
+  NB_SYM(CreateProgram) NB_SYM(CompileProgram) NB_SYM(GetCUBINSize) NB_SYM(GetCUBIN) NB_SYM(GetProgramLogSize) NB_SYM(GetProgramLog) NB_SYM(DestroyProgram)
+#undef NB_SYM
+  n.ok = true;
+  return n;
+}
+
+const char* kPrelude = R"SRC(
+typedef unsigned int u32; typedef unsigned long long u64;
+#define P31 0x7fffffffu
+struct Q { u32 c0, c1, c2, c3; };
+__device__ __forceinline__ u32 mn(u32 a, u32 b) { return a < b ? a : b; }
+__device__ __forceinline__ u32 add(u32 a, u32 b) { u32 s = a + b; return mn(s, s - P31); }
+__device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return mn(d, d + P31); }
+__device__ __forceinline__ u32 neg(u32 a) { return a ? P31 - a : 0u; }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 p = (u64)a * b; u32 s = ((u32)p & P31) + (u32)(p >> 31); return mn(s, s - P31); }
+__device__ __forceinline__ Q qadd(Q x, Q y) { return Q{add(x.c0, y.c0), add(x.c1, y.c1), add(x.c2, y.c2), add(x.c3, y.c3)}; }
+__device__ __forceinline__ Q qsub(Q x, Q y) { return Q{sub(x.c0, y.c0), sub(x.c1, y.c1), sub(x.c2, y.c2), sub(x.c3, y.c3)}; }
+__device__ __forceinline__ Q qneg(Q x) { return Q{neg(x.c0), neg(x.c1), neg(x.c2), neg(x.c3)}; }
+__device__ __forceinline__ Q qmulb(Q x, u32 b) { return Q{mul(x.c0, b), mul(x.c1, b), mul(x.c2, b), mul(x.c3, b)}; }
+__device__ __forceinline__ Q qaddb(Q x, u32 b) { x.c0 = add(x.c0, b); return x; }
+__device__ __forceinline__ Q qsubb(Q x, u32 b) { x.c0 = sub(x.c0, b); return x; }
+__device__ __noinline__ Q qmul(Q x, Q y) {
+  // (a + bu)(c + du) = (ac + R bd) + (ad + bc)u,  R = 2 + i   (same formula as m31.cuh qm31_mul)
+  u32 ac0 = sub(mul(x.c0, y.c0), mul(x.c1, y.c1)), ac1 = add(mul(x.c0, y.c1), mul(x.c1, y.c0));
+  u32 bd0 = sub(mul(x.c2, y.c2), mul(x.c3, y.c3)), bd1 = add(mul(x.c2, y.c3), mul(x.c3, y.c2));
+  u32 r0 = sub(add(bd0, bd0), bd1), r1 = add(bd0, add(bd1, bd1));
+  u32 ad0 = sub(mul(x.c0, y.c2), mul(x.c1, y.c3)), ad1 = add(mul(x.c0, y.c3), mul(x.c1, y.c2));
+  u32 bc0 = sub(mul(x.c2, y.c0), mul(x.c3, y.c1)), bc1 = add(mul(x.c2, y.c1), mul(x.c3, y.c0));
+  return Q{add(ac0, r0), add(ac1, r1), add(ad0, bc0), add(ad1, bc1)};
+}
+__device__ __forceinline__ Q ldq(const u32* p) { return Q{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}; }
+)SRC";
+
+std::string gen_source(const AirComponent& c) {
+  std::ostringstream o;
+  o << kPrelude;
+  const u32 EL = c.eval_log(), DL = c.log_size;
+  // offset_bit_reversed_circle_domain_index with the domain sizes baked in
+  o << "__device__ __forceinline__ u32 offrow(u32 i, int off) { const u32 EL = " << EL << ", DL = " << DL << ";\n"
+    << "  u32 prev = __brev(i) >> (32 - EL); u32 half = 1u << (EL - 1); long long step = (long long)off * (1ll << (EL - DL - 1)); long long v;\n"
+    << "  if (prev < half) { v = ((long long)prev + step) % (long long)half; if (v < 0) v += half; }\n"
+    << "  else { v = ((long long)prev - step) % (long long)half; if (v < 0) v += half; v += half; }\n"
+    << "  return __brev((u32)v) >> (32 - EL); }\n";
+  const u32 nb = c.n_base_regs ? c.n_base_regs : 1, ne = c.n_ext_regs ? c.n_ext_regs : 1;
+  o << "struct St { u32 b[" << nb << "]; Q e[" << ne << "]; Q rr; };\n";
+  auto ld = [&](u32 m) {
+    std::ostringstream s;
+    if (c.masks[m].off == 0) s << "__ldg(cols[" << m << "] + row)";
+    else s << "__ldg(cols[" << m << "] + offrow(row, " << c.masks[m].off << "))";
+    return s.str();
+  };
+  const size_t CH = 250;
+  size_t n_chunks = (c.prog.size() + CH - 1) / CH;
+  u32 k = 0;
+  for (size_t ci = 0; ci < n_chunks; ++ci) {
+    o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff, u32 row) {\n";
+    o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q rr = s.rr;\n";
+    o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
+    for (size_t pc = ci * CH; pc < std::min(c.prog.size(), (ci + 1) * CH); ++pc) {
+      const AirInstr& in = c.prog[pc];
+      o << "  ";
+      switch (in.op) {
+        case OP_LOADM: o << "b[" << in.dst << "] = " << ld(in.a) << ";"; break;
+        case OP_CONSTB: o << "b[" << in.dst << "] = " << in.a << "u;"; break;
+        case OP_ADDB: o << "b[" << in.dst << "] = add(b[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_SUBB: o << "b[" << in.dst << "] = sub(b[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_MULB: o << "b[" << in.dst << "] = mul(b[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_NEGB: o << "b[" << in.dst << "] = neg(b[" << in.a << "]);"; break;
+        case OP_PARAME: o << "e[" << in.dst << "] = ldq(params + " << 4 * in.a << ");"; break;
+        case OP_ADDE: o << "e[" << in.dst << "] = qadd(e[" << in.a << "], e[" << in.b << "]);"; break;
+        case OP_SUBE: o << "e[" << in.dst << "] = qsub(e[" << in.a << "], e[" << in.b << "]);"; break;
+        case OP_MULE: o << "e[" << in.dst << "] = qmul(e[" << in.a << "], e[" << in.b << "]);"; break;
+        case OP_NEGE: o << "e[" << in.dst << "] = qneg(e[" << in.a << "]);"; break;
+        case OP_ADDEB: o << "e[" << in.dst << "] = qaddb(e[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_SUBEB: o << "e[" << in.dst << "] = qsubb(e[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_MULEB: o << "e[" << in.dst << "] = qmulb(e[" << in.a << "], b[" << in.b << "]);"; break;
+        case OP_BTOE: o << "e[" << in.dst << "] = Q{b[" << in.a << "], 0u, 0u, 0u};"; break;
+        case OP_LOADME: o << "e[" << in.dst << "] = Q{" << ld(in.a) << ", " << ld(in.a + 1) << ", " << ld(in.a + 2) << ", " << ld(in.a + 3) << "};"; break;
+        case OP_CONSTRB: o << "rr = qadd(rr, qmulb(ldq(coeff + " << 4 * k << "), b[" << in.a << "]));"; ++k; break;
+        case OP_CONSTRE: o << "rr = qadd(rr, qmul(ldq(coeff + " << 4 * k << "), e[" << in.a << "]));"; ++k; break;
+        default: break;
+      }
+      o << "\n";
+    }
+    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.rr = rr;\n}\n";
+  }
+  o << "extern \"C\" __global__ void __launch_bounds__(128) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
+    << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3) {\n"
+    << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
+    << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
+  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row);\n";
+  o << "  const u32 di = __ldg(dinv + (row >> " << DL << "));\n"
+    << "  a0[row] = add(a0[row], mul(s.rr.c0, di)); a1[row] = add(a1[row], mul(s.rr.c1, di));\n"
+    << "  a2[row] = add(a2[row], mul(s.rr.c2, di)); a3[row] = add(a3[row], mul(s.rr.c3, di));\n}\n";
+  return o.str();
+}
+}  // namespace
+
+bool jit_enabled() {
+  const char* e = getenv("NB200_JIT");
+  if (e && e[0] == '0') return false;
+  return nvrtc().ok;
+}
+
+void jit_release(JitKernel& jk) {
+  if (jk.lib) cudaLibraryUnload((cudaLibrary_t)jk.lib);
+  jk = JitKernel();
+}
+
+nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out) {
+  *out = JitKernel();
+  Nvrtc& n = nvrtc();
+  if (!n.ok) return set_err(ctx, NB200_ERR_STATE, "jit: libnvrtc not available");
+  if (c.eval_log() < 7) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");  // grid must be a whole number of 128-thread blocks
+  std::string src = gen_source(c);
+  nvrtcProgram prog;
+  if (n.CreateProgram(&prog, src.c_str(), "nb200_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return set_err(ctx, NB200_ERR_STATE, "jit: nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  nvrtcResult r = n.CompileProgram(prog, 3, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t ls = 0; n.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0'); if (ls) n.GetProgramLog(prog, &log[0]);
+    n.DestroyProgram(&prog);
+    return set_err(ctx, NB200_ERR_STATE, "jit: compile failed: " + log.substr(0, 2000));
+  }
+  size_t cs = 0; n.GetCUBINSize(prog, &cs);
+  std::vector<char> cubin(cs);
+  n.GetCUBIN(prog, cubin.data());
+  n.DestroyProgram(&prog);
+  cudaLibrary_t lib;
+  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryLoadData: ") + cudaGetErrorString(e));
+  cudaKernel_t k;
+  e = cudaLibraryGetKernel(&k, lib, "nbjit");
+  if (e != cudaSuccess) { cudaLibraryUnload(lib); return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryGetKernel: ") + cudaGetErrorString(e)); }
+  out->lib = (void*)lib; out->kernel = (void*)k; out->log_size = c.log_size; out->eval_log = c.eval_log();
+  return NB200_OK;
+}
+
+nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4]) {
+  size_t rows = (size_t)1 << jk.eval_log;
+  u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
+  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3};
+  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / 128)), dim3(128), args, 0, ctx->stream);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));
+  return NB200_OK;
+}
+
+}  // namespace nb

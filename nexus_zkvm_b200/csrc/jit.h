@@ -1,0 +1,21 @@
+// NVRTC specialisation of AIR constraint programs (see jit.cu).
+#pragma once
+#include "common.cuh"
+#include "air.h"
+
+namespace nb {
+
+struct JitKernel {
+  void* lib = nullptr;     // cudaLibrary_t
+  void* kernel = nullptr;  // cudaKernel_t
+  u32 log_size = 0, eval_log = 0;
+  bool tried = false;      // compilation attempted (failed attempts fall back to the interpreter)
+};
+
+bool jit_enabled();
+nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out);
+nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff,
+                                    const u32* d_dinv, u32* const acc[4]);
+void jit_release(JitKernel& jk);
+
+}  // namespace nb

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "air.h"
+#include "jit.h"
 #include <utility>
 
 namespace nb {
@@ -24,7 +25,7 @@ nb200_status add_inplace(nb200_ctx* ctx, u32* a, const u32* b, size_t n);
 nb200_status grind(nb200_ctx* ctx, const uint8_t digest[32], u32 pow_bits, uint64_t* nonce_out);
 
 nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                             const std::vector<qm31>& coeffs, u32* const acc[4]);
+                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk = nullptr);
 nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
                             u32* d_out, qm31* claimed);
 

@@ -15,7 +15,11 @@
 #include <cstring>
 
 struct nb200_channel { nb::HostChannel ch; };
-struct nb200_air { nb::AirProgram prog; };
+struct nb200_air {
+  nb::AirProgram prog;
+  std::vector<nb::JitKernel> jit;  // per component, compiled on first use (NVRTC); empty kernel = interpreter
+  ~nb200_air() { for (auto& j : jit) nb::jit_release(j); }
+};
 
 namespace nb {
 
@@ -231,8 +235,10 @@ static nb200_status positions_and_witness(nb200_ctx* ctx, const nb200_cols* col4
 static qm31 load_param(const u32* p) { return qm31_make(p[0], p[1], p[2], p[3]); }
 
 // stwo::prover::prove
-nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vector<qm31>& params, HostChannel& ch, std::vector<uint8_t>& proof_bytes) {
+nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm31>& params, HostChannel& ch, std::vector<uint8_t>& proof_bytes) {
   nb200_ctx* ctx = s->ctx;
+  const AirProgram& air = air_h->prog;
+  if (air_h->jit.size() != air.comps.size()) air_h->jit.resize(air.comps.size());
   NB_ARG(ctx, s->trees.size() == 3, "prove: the preprocessed, main and interaction trees must be committed first");
   NB_ARG(ctx, params.size() == air.n_params, "prove: parameter table size");
   const u32 blow = s->log_blowup;
@@ -284,7 +290,17 @@ nb200_status prove_impl(nb200_scheme* s, const AirProgram& air, const std::vecto
       std::vector<qm31> coeff(c.n_constraints);
       for (u32 k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
       u32* accp[4] = {acc[elog]->col(0), acc[elog]->col(1), acc[elog]->col(2), acc[elog]->col(3)};
-      st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp);
+      JitKernel& jk = air_h->jit[&c - &air.comps[0]];
+      if (!jk.tried) {
+        jk.tried = true;
+        if (jit_enabled() && c.prog.size() >= 64) {
+          trace_mark(ctx, nullptr);
+          nb200_status js = jit_compile_constraints(ctx, c, &jk);
+          if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
+          trace_mark(ctx, "jit compile (one-time)");
+        }
+      }
+      st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jk.kernel ? &jk : nullptr);
     }
     g0 += c.n_constraints;
     free_ext();
@@ -700,7 +716,7 @@ nb200_status nb200_prove(nb200_scheme* s, const nb200_air* air, const uint32_t* 
   std::vector<qm31> p(n_params);
   if (n_params) memcpy(p.data(), params, n_params * 16);
   std::vector<uint8_t> bytes;
-  NB_TRY(prove_impl(s, air->prog, p, channel->ch, bytes));
+  NB_TRY(prove_impl(s, const_cast<nb200_air*>(air), p, channel->ch, bytes));
   uint8_t* o = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
   memcpy(o, bytes.data(), bytes.size());
   *proof_out = o; *proof_len = bytes.size();

@@ -109,3 +109,16 @@ def test_transcript_flavours_match_oracle(merkle_hash, draw_sep):
     finally:
         orc.set_flavor()
         ctx.close()
+
+
+def test_interpreter_and_jit_kernels_agree(backend, monkeypatch):
+    # the constraint program runs either through the NVRTC-specialised kernel (default when libnvrtc is present) or the
+    # bytecode interpreter (NB200_JIT=0); both must give the oracle's bytes
+    m = M.AddMachine(log_size=9, n_lanes=2)
+    cols, mult = m.fill_main_trace(seed=41)
+    o_proof, _, _ = M.prove(m, OracleBackend(), cols, mult)
+    monkeypatch.setenv("NB200_JIT", "0")
+    i_proof, _, _ = M.prove(m, backend, cols, mult)
+    monkeypatch.setenv("NB200_JIT", "1")
+    j_proof, _, _ = M.prove(m, backend, cols, mult)
+    assert i_proof == o_proof and j_proof == o_proof
