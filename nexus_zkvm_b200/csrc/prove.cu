@@ -294,7 +294,7 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
       if (!jk.tried) {
         jk.tried = true;
         if (jit_enabled() && c.prog.size() >= 64) {
-          trace_mark(ctx, nullptr);
+          trace_mark(ctx, "constraints: extend columns");
           nb200_status js = jit_compile_constraints(ctx, c, &jk);
           if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
           trace_mark(ctx, "jit compile (one-time)");

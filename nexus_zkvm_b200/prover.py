@@ -2,6 +2,7 @@
 interaction-trace generation and stwo::prover::prove — the surface /root/reference prover/src/machine.rs:197-290 drives.
 `CudaBackend` plugs into nexus_zkvm_b200.machine.prove()."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -78,7 +79,7 @@ class CommitmentSchemeProver:
 
     def __init__(self, ctx, air_words, config):
         self.ctx, self.config = ctx, config
-        self.air = Air(ctx, air_words)
+        self.air = air_words if isinstance(air_words, Air) else Air(ctx, air_words)
         self._h = C.c_void_p()
         ctx._chk(lib().nb200_scheme_new(ctx._h, C.c_uint32(config["pow_bits"]), C.c_uint32(config["log_blowup"]),
                                         C.c_uint32(config["log_last"]), C.c_uint32(config["n_queries"]), C.byref(self._h)))
@@ -179,12 +180,18 @@ class CudaBackend:
 
     def __init__(self, ctx=None, device=0):
         self.ctx = ctx or Context(device)
+        self._airs = {}
 
     def channel(self):
         return Channel(self.ctx)
 
     def prover(self, words, config):
-        return CommitmentSchemeProver(self.ctx, words, config)
+        # a loaded AIR (and its NVRTC-specialised kernels) is reused across proofs of the same machine
+        key = (np.asarray(words, dtype=np.uint32).tobytes(), os.environ.get("NB200_JIT", ""))
+        air = self._airs.get(key)
+        if air is None:
+            air = self._airs[key] = Air(self.ctx, words)
+        return CommitmentSchemeProver(self.ctx, air, config)
 
 
 def smoke(ctx):
