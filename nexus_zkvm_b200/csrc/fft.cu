@@ -39,6 +39,7 @@ struct FftPass {
   u32 cb;             // columns per CTA
   u32 scale;          // multiply outputs by this (interpolate last pass) if apply_scale
   u32 apply_scale;
+  u32 ztop;           // forward transforms of zero-extended input: layers >= ztop are copies (= log2 of the source length)
 };
 
 __device__ __forceinline__ void butterfly(u32& v0, u32& v1, u32 t) {
@@ -96,19 +97,28 @@ __device__ __forceinline__ void ibutterfly_dbl(u32& v0, u32& v1, u32 it2) {
 }
 
 template <bool INV>
-__device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const int jlo) {
-  // tw holds DOUBLED twiddles
+__device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const int jlo, const u32 triv = 0u) {
+  // tw holds DOUBLED twiddles.  triv bit j (forward only): layer j of this round sits at or above the zero-extension
+  // boundary, its odd inputs are known zeros, so the butterfly degenerates to a copy (no arithmetic).
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const int j = INV ? jj : 3 - jj;
     if (j >= jlo) {
+      if (!INV && ((triv >> j) & 1u)) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
-        const int k1 = k0 | (1 << j);
-        const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
-        if (INV) ibutterfly_dbl(v[k0], v[k1], tw[off]);
-        else butterfly_dbl(v[k0], v[k1], tw[off]);
+        for (int m = 0; m < 8; ++m) {
+          const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
+          v[k0 | (1 << j)] = v[k0];
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
+          const int k1 = k0 | (1 << j);
+          const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
+          if (INV) ibutterfly_dbl(v[k0], v[k1], tw[off]);
+          else butterfly_dbl(v[k0], v[k1], tw[off]);
+        }
       }
     }
   }
@@ -166,6 +176,11 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
     const int b = ri < NFULL ? W + 4 * ri : T - 4;
     const int jlo = ri < NFULL ? 0 : 4 - REM;
     const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
+    u32 triv = 0u;
+    if (!INV) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (lo + b + j - W >= p.ztop) triv |= 1u << j;
+    }
     // twiddles: layer j of the round is global layer i = lo + b + j - W; the (8 >> j) twiddles of a thread are contiguous
     u32 tw[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
           uint4 q2 = *reinterpret_cast<uint4*>(smc + a2), q3 = *reinterpret_cast<uint4*>(smc + a3);
           v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
           v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w; v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
-          radix16<INV>(v, tw, jlo);
+          radix16<INV>(v, tw, jlo, triv);
           *reinterpret_cast<uint4*>(smc + a0) = make_uint4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<uint4*>(smc + a1) = make_uint4(v[4], v[5], v[6], v[7]);
           *reinterpret_cast<uint4*>(smc + a2) = make_uint4(v[8], v[9], v[10], v[11]);
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
           u32 v[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = smc[addr[k]];
-          radix16<INV>(v, tw, jlo);
+          radix16<INV>(v, tw, jlo, triv);
 #pragma unroll
           for (int k = 0; k < 16; ++k) smc[addr[k]] = v[k];
         }
@@ -485,7 +500,7 @@ static bool launch_fast(nb200_ctx* ctx, const FftPass& p, nb200_status* st) {
 
 template <bool INV>
 static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* src, size_t src_stride, size_t src_len,
-                                u32* dst, size_t dst_stride, size_t n_cols, u32 n, bool scale) {
+                                u32* dst, size_t dst_stride, size_t n_cols, u32 n, bool scale, u32 ztop = 0xffffffffu) {
   FftPass p;
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = src_len;
   p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
@@ -497,7 +512,7 @@ static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* s
   p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
   p.cb = pl.T >= 13 ? 2 : 4;
   if (p.cb > n_cols) p.cb = (u32)n_cols;
-  p.scale = 0; p.apply_scale = 0;
+  p.scale = 0; p.apply_scale = 0; p.ztop = ztop < n ? ztop : n;
   if (scale) { p.apply_scale = 1; p.scale = m31_inv((u32)(1u << n) % P31); }
   // 128-bit staging needs 16-byte aligned columns
   bool aligned = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15u) == 0 && (src_stride % 4 == 0) && (dst_stride % 4 == 0) && (src_len % 4 == 0);
@@ -573,7 +588,7 @@ nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst,
   plan_passes(n, plan);
   for (size_t k = plan.size(); k-- > 0;) {
     bool first = (k + 1 == plan.size());
-    if (first) NB_TRY(launch_pass<false>(ctx, plan[k], src, slen, slen, dst, len, n_cols, n, false));
+    if (first) NB_TRY(launch_pass<false>(ctx, plan[k], src, slen, slen, dst, len, n_cols, n, false, src_log));
     else NB_TRY(launch_pass<false>(ctx, plan[k], dst, len, len, dst, len, n_cols, n, false));
   }
   return NB200_OK;

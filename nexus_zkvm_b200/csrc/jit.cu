@@ -148,7 +148,7 @@ void jit_release(JitKernel& jk) {
 }
 
 nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out) {
-  *out = JitKernel();
+  out->lib = nullptr; out->kernel = nullptr; out->tried = true;
   Nvrtc& n = nvrtc();
   if (!n.ok) return set_err(ctx, NB200_ERR_STATE, "jit: libnvrtc not available");
   if (c.eval_log() < 7) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");  // grid must be a whole number of 128-thread blocks
