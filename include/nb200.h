@@ -177,6 +177,34 @@ nb200_status nb200_gen_interaction_trace(nb200_ctx*, const nb200_air*, uint32_t 
 nb200_status nb200_prove(nb200_scheme*, const nb200_air*, const uint32_t* params, size_t n_params, nb200_channel*,
                          uint8_t** proof_out, size_t* proof_len);
 
+/* ---- backend-trait level operations ---------------------------------------------------------------------
+ * The per-trait surface a Rust `struct CudaBackend;` shim binds when it implements Stwo's backend traits one by one
+ * instead of calling the coarse nb200_prove.  nb200_prove runs exactly this code.  A "secure column"
+ * (SecureColumnByCoords) is a batch of 4 coordinate columns. */
+/* ComponentProver::<B>::evaluate_constraint_quotients_on_domain for one component (built at machine.rs:265-285): extend
+ * the committed polynomials the component reads to CanonicCoset(log_size + log_expand).circle_domain(), evaluate
+ * sum_k coeffs[k] * constraint_k / vanishing on every row and ADD into accum (4 columns of that domain size).
+ * coeffs = n_coeffs QM31 (= the component's n_constraints random-coefficient powers, first constraint first). */
+nb200_status nb200_constraint_quotients(nb200_scheme*, const nb200_air*, uint32_t component, const uint32_t* params, size_t n_params,
+                                        const uint32_t* coeffs, size_t n_coeffs, nb200_cols* accum);
+/* AccumulationOps::accumulate: a += b (element-wise, M31), same shapes */
+nb200_status nb200_accumulate(nb200_ctx*, nb200_cols* a, const nb200_cols* b);
+/* QuotientOps::accumulate_quotients (DEEP quotients) on CanonicCoset(log_size).circle_domain(): columns are numbered
+ * through the batches in order; sample batch b = OODS point {x[4], y[4]} + entries [first_entry, first_entry+n_entries)
+ * of (column, sampled value).  Out: a new secure column (4 x 2^log_size). */
+typedef struct { uint32_t point[8]; size_t first_entry, n_entries; } nb200_sample_batch;
+typedef struct { uint32_t column; uint32_t value[4]; } nb200_sample_entry;
+nb200_status nb200_fri_quotients(nb200_ctx*, const nb200_cols* const* batches, size_t n_batches, uint32_t log_size,
+                                 const nb200_sample_batch* sample_batches, size_t n_sample_batches,
+                                 const nb200_sample_entry* entries, size_t n_entries, const uint32_t random_coeff[4], nb200_cols** out);
+/* FriOps::fold_circle_into_line: dst = dst * alpha^2 + fold(src); src = secure column on CanonicCoset(k).circle_domain(),
+ * dst = secure column of 2^(k-1) values on LineDomain(Coset::half_odds(k-1)) */
+nb200_status nb200_fold_circle_into_line(nb200_ctx*, nb200_cols* dst, const nb200_cols* src, const uint32_t alpha[4]);
+/* FriOps::fold_line: src on LineDomain(Coset::half_odds(k)) (bit-reversed) -> new secure column of 2^(k-1) values */
+nb200_status nb200_fold_line(nb200_ctx*, const nb200_cols* src, const uint32_t alpha[4], nb200_cols** dst_out);
+/* GrindOps::grind: smallest nonce with >= pow_bits trailing zero bits in H(digest, nonce) (channel digest in, nonce out) */
+nb200_status nb200_grind(nb200_ctx*, const uint8_t digest[32], uint32_t pow_bits, uint64_t* nonce_out);
+
 #ifdef __cplusplus
 }
 #endif

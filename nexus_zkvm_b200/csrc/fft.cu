@@ -124,7 +124,8 @@ __device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const
   }
 }
 
-template <bool INV, int T, int W, int CB>
+// NZ: (forward, top pass of a zero-extended input) the top NZ layers of the pass have all-zero odd inputs -> copies
+template <bool INV, int T, int W, int CB, int NZ>
 __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kernel(const FftPass p) {
   extern __shared__ __align__(16) u32 sm[];
   constexpr int L = T - W;
@@ -177,9 +178,9 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
     const int jlo = ri < NFULL ? 0 : 4 - REM;
     const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
     u32 triv = 0u;
-    if (!INV) {
+    if (!INV && NZ > 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (lo + b + j - W >= p.ztop) triv |= 1u << j;
+      for (int j = 0; j < 4; ++j) if (b + j - W >= L - NZ) triv |= 1u << j;
     }
     // twiddles: layer j of the round is global layer i = lo + b + j - W; the (8 >> j) twiddles of a thread are contiguous
     u32 tw[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -473,17 +474,17 @@ static void plan_passes(u32 n, std::vector<PassPlan>& out) {
   }
 }
 
-template <bool INV, int T, int W, int CB>
+template <bool INV, int T, int W, int CB, int NZ>
 static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
   constexpr int threads = 1 << (T - 4);
   constexpr size_t smem = (size_t)CB << (T + 2);
   static bool attr_set = false;
   if (!attr_set) {
-    NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_kernel<INV, T, W, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_kernel<INV, T, W, CB, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB - 1) / CB));
-  fft_tile_kernel<INV, T, W, CB><<<grid, threads, smem, ctx->stream>>>(p);
+  fft_tile_kernel<INV, T, W, CB, NZ><<<grid, threads, smem, ctx->stream>>>(p);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
@@ -491,10 +492,20 @@ static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
 // returns true if a specialised kernel exists for (T, W)
 template <bool INV>
 static bool launch_fast(nb200_ctx* ctx, const FftPass& p, nb200_status* st) {
-#define NB_CASE(TT, WW, CBB) if (p.T == TT && p.W == WW) { *st = launch_tile<INV, TT, WW, CBB>(ctx, p); return true; }
+  // zero-extension specialisations exist for the strided (top) passes of forward transforms only
+  const u32 nz = (!INV && p.W > 0 && p.lo + p.T - p.W == p.n && p.ztop < p.n) ? (p.n - p.ztop >= 2 ? 2u : 1u) : 0u;
+#define NB_CASE(TT, WW, CBB) if (p.T == TT && p.W == WW) { *st = launch_tile<INV, TT, WW, CBB, 0>(ctx, p); return true; }
+#define NB_CASEZ(TT, WW, CBB)                                                                          \
+  if (p.T == TT && p.W == WW) {                                                                        \
+    if (INV || nz == 0) *st = launch_tile<INV, TT, WW, CBB, 0>(ctx, p);                                \
+    else if (nz == 1) *st = launch_tile<false, TT, WW, CBB, 1>(ctx, p);                                \
+    else *st = launch_tile<false, TT, WW, CBB, 2>(ctx, p);                                             \
+    return true;                                                                                       \
+  }
   NB_CASE(9, 0, 4) NB_CASE(10, 0, 4) NB_CASE(11, 0, 4) NB_CASE(12, 0, 4) NB_CASE(13, 0, 2)
-  NB_CASE(12, 4, 4) NB_CASE(12, 5, 4) NB_CASE(12, 6, 4) NB_CASE(12, 7, 4) NB_CASE(12, 8, 4) NB_CASE(13, 4, 2)
+  NB_CASEZ(12, 4, 4) NB_CASEZ(12, 5, 4) NB_CASEZ(12, 6, 4) NB_CASEZ(12, 7, 4) NB_CASEZ(12, 8, 4) NB_CASEZ(13, 4, 2)
 #undef NB_CASE
+#undef NB_CASEZ
   return false;
 }
 

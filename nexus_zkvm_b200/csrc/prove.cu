@@ -234,6 +234,88 @@ static nb200_status positions_and_witness(nb200_ctx* ctx, const nb200_cols* col4
 
 static qm31 load_param(const u32* p) { return qm31_make(p[0], p[1], p[2], p[3]); }
 
+// ComponentProver::evaluate_constraint_quotients_on_domain for one component: extend every batch the component reads to
+// its evaluation domain, run the (JIT-specialised or interpreted) constraint kernel, accumulate into `accum` (4 columns).
+nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_idx, const u32* d_params, const std::vector<qm31>& coeff, nb200_cols* accum) {
+  nb200_ctx* ctx = s->ctx;
+  const AirProgram& air = air_h->prog;
+  NB_ARG(ctx, comp_idx < air.comps.size(), "constraint quotients: component index");
+  if (air_h->jit.size() != air.comps.size()) air_h->jit.resize(air.comps.size());
+  const AirComponent& c = air.comps[comp_idx];
+  const u32 elog = c.eval_log();
+  NB_ARG(ctx, accum && accum->n_cols == 4 && accum->log_size == elog, "constraint quotients: accumulator must be 4 columns of the evaluation domain size");
+  NB_ARG(ctx, coeff.size() == c.n_constraints, "constraint quotients: one coefficient per constraint");
+  NB_TRY(twiddles_prepare(ctx, elog));
+  std::map<std::pair<u32, u32>, nb200_cols*> ext;
+  auto free_ext = [&]() { for (auto& kv : ext) nb200_cols_free(ctx, kv.second); ext.clear(); };
+  std::vector<const u32*> mask_cols(c.masks.size());
+  nb200_status st = NB200_OK;
+  for (size_t m = 0; m < c.masks.size() && st == NB200_OK; ++m) {
+    const AirMask& mk = c.masks[m];
+    if (mk.tree >= s->trees.size() || mk.col >= s->trees[mk.tree].cols.size()) { st = set_err(ctx, NB200_ERR_ARG, "prove: AIR references a column that was not committed"); break; }
+    const SchemeTree::ColLoc& loc = s->trees[mk.tree].cols[mk.col];
+    if (loc.log != c.log_size) { st = set_err(ctx, NB200_ERR_ARG, "prove: column size differs from its component's log_size"); break; }
+    auto key = std::make_pair(mk.tree, loc.batch);
+    if (!ext.count(key)) {
+      const nb200_cols* co = s->trees[mk.tree].coeffs[loc.batch];
+      nb200_cols* e = nullptr;
+      st = nb200_cols_alloc(ctx, co->n_cols, elog, &e);
+      if (st != NB200_OK) break;
+      ext[key] = e;
+      st = fft_evaluate(ctx, co->d, co->log_size, e->d, elog, co->n_cols);
+    }
+    if (st == NB200_OK) mask_cols[m] = ext[key]->col(loc.idx);
+  }
+  if (st == NB200_OK) {
+    u32* accp[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
+    JitKernel& jk = air_h->jit[comp_idx];
+    if (!jk.tried) {
+      jk.tried = true;
+      if (jit_enabled() && c.prog.size() >= 64) {
+        trace_mark(ctx, "constraints: extend columns");
+        nb200_status js = jit_compile_constraints(ctx, c, &jk);
+        if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
+        trace_mark(ctx, "jit compile (one-time)");
+      }
+    }
+    st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jk.kernel ? &jk : nullptr);
+  }
+  free_ext();
+  return st;
+}
+
+// QuotientOps::accumulate_quotients on CanonicCoset(log_size).circle_domain(): out (4 columns) = sum over the sample batches
+struct SampleBatch { qpoint p; std::vector<std::pair<const u32*, qm31>> cols; };
+nb200_status accumulate_quotients(nb200_ctx* ctx, u32 lg, const std::vector<SampleBatch>& hb, qm31 q_coeff, u32* out) {
+  std::vector<QBatchDev> qb(hb.size()); std::vector<QEntryDev> qe;
+  for (size_t b = 0; b < hb.size(); ++b) {
+    QBatchDev& B = qb[b];
+    const qpoint& p = hb[b].p;
+    B.prx[0] = p.x.c[0]; B.prx[1] = p.x.c[1]; B.pix[0] = p.x.c[2]; B.pix[1] = p.x.c[3];
+    B.pry[0] = p.y.c[0]; B.pry[1] = p.y.c[1]; B.piy[0] = p.y.c[2]; B.piy[1] = p.y.c[3];
+    qm31 alpha = qm31_one(), sa = qm31_zero(), sb = qm31_zero();
+    B.first = (u32)qe.size(); B.count = (u32)hb[b].cols.size();
+    for (auto& cv : hb[b].cols) {
+      alpha = qm31_mul(alpha, q_coeff);
+      // complex_conjugate_line_coeffs
+      qm31 a = qm31_sub(qm31_conj(cv.second), cv.second);
+      qm31 c = qm31_sub(qm31_conj(p.y), p.y);
+      qm31 bq = qm31_sub(qm31_mul(cv.second, c), qm31_mul(a, p.y));
+      sa = qm31_add(sa, qm31_mul(alpha, a)); sb = qm31_add(sb, qm31_mul(alpha, bq));
+      qm31 ac = qm31_mul(alpha, c);
+      QEntryDev e; e.col = cv.first; memcpy(e.c, ac.c, 16); e.pad[0] = e.pad[1] = 0;
+      qe.push_back(e);
+    }
+    memcpy(B.A, sa.c, 16); memcpy(B.B, sb.c, 16);
+    qm31 bc = qm31_pow(q_coeff, hb[b].cols.size());
+    memcpy(B.coeff, bc.c, 16);
+  }
+  ColsGuard dom(ctx);
+  NB_TRY(nb200_cols_alloc(ctx, 2, lg, &dom.c));
+  NB_TRY(domain_points(ctx, lg, dom.c->col(0), dom.c->col(1)));
+  return quotients_launch(ctx, qb.data(), qb.size(), qe.data(), qe.size(), dom.c->col(0), dom.c->col(1), lg, out);
+}
+
 // stwo::prover::prove
 nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm31>& params, HostChannel& ch, std::vector<uint8_t>& proof_bytes) {
   nb200_ctx* ctx = s->ctx;
@@ -260,28 +342,8 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
   size_t g0 = 0;
   for (const AirComponent& c : air.comps) {
     const u32 elog = c.eval_log();
-    // evaluate every batch this component reads on its evaluation domain
-    std::map<std::pair<u32, u32>, nb200_cols*> ext;
-    auto free_ext = [&]() { for (auto& kv : ext) nb200_cols_free(ctx, kv.second); ext.clear(); };
-    std::vector<const u32*> mask_cols(c.masks.size());
     nb200_status st = NB200_OK;
-    for (size_t m = 0; m < c.masks.size() && st == NB200_OK; ++m) {
-      const AirMask& mk = c.masks[m];
-      if (mk.col >= s->trees[mk.tree].cols.size()) { st = set_err(ctx, NB200_ERR_ARG, "prove: AIR references a column that was not committed"); break; }
-      const SchemeTree::ColLoc& loc = s->trees[mk.tree].cols[mk.col];
-      if (loc.log != c.log_size) { st = set_err(ctx, NB200_ERR_ARG, "prove: column size differs from its component's log_size"); break; }
-      auto key = std::make_pair(mk.tree, loc.batch);
-      if (!ext.count(key)) {
-        const nb200_cols* co = s->trees[mk.tree].coeffs[loc.batch];
-        nb200_cols* e = nullptr;
-        st = nb200_cols_alloc(ctx, co->n_cols, elog, &e);
-        if (st != NB200_OK) break;
-        ext[key] = e;
-        st = fft_evaluate(ctx, co->d, co->log_size, e->d, elog, co->n_cols);
-      }
-      if (st == NB200_OK) mask_cols[m] = ext[key]->col(loc.idx);
-    }
-    if (st == NB200_OK && !acc.count(elog)) {
+    if (!acc.count(elog)) {
       nb200_cols* a = nullptr;
       st = nb200_cols_alloc(ctx, 4, elog, &a);
       if (st == NB200_OK) { acc[elog] = a; if (cudaMemsetAsync(a->d, 0, ((size_t)16) << elog, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "memset"); }
@@ -289,21 +351,9 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     if (st == NB200_OK) {
       std::vector<qm31> coeff(c.n_constraints);
       for (u32 k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
-      u32* accp[4] = {acc[elog]->col(0), acc[elog]->col(1), acc[elog]->col(2), acc[elog]->col(3)};
-      JitKernel& jk = air_h->jit[&c - &air.comps[0]];
-      if (!jk.tried) {
-        jk.tried = true;
-        if (jit_enabled() && c.prog.size() >= 64) {
-          trace_mark(ctx, "constraints: extend columns");
-          nb200_status js = jit_compile_constraints(ctx, c, &jk);
-          if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
-          trace_mark(ctx, "jit compile (one-time)");
-        }
-      }
-      st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jk.kernel ? &jk : nullptr);
+      st = component_quotients(s, air_h, &c - &air.comps[0], d_params, coeff, acc[elog]);
     }
     g0 += c.n_constraints;
-    free_ext();
     if (st != NB200_OK) { free_acc(); dfree(ctx, d_params); return st; }
   }
   trace_mark(ctx, "constraint quotients");
@@ -403,47 +453,20 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     size_t j = i; while (j < all.size() && all[j].log == all[i].log) ++j;
     const u32 lg = all[i].log;
     // ColumnSampleBatch::new_vec: group samples by point, first-seen order                   [risk: IndexMap vs BTreeMap]
-    struct HB { qpoint p; std::vector<std::pair<size_t, qm31>> cols; };
-    std::vector<HB> hb;
+    std::vector<SampleBatch> hb;
     for (size_t k = i; k < j; ++k) {
       const CRef& r = all[k];
       for (size_t pi = 0; pi < points[r.t][r.g].size(); ++pi) {
         const qpoint& p = points[r.t][r.g][pi];
         size_t b = 0;
         for (; b < hb.size(); ++b) if (qm31_eq(hb[b].p.x, p.x) && qm31_eq(hb[b].p.y, p.y)) break;
-        if (b == hb.size()) hb.push_back(HB{p, {}});
-        hb[b].cols.push_back({k, sampled[r.t][r.g][pi]});
+        if (b == hb.size()) hb.push_back(SampleBatch{p, {}});
+        hb[b].cols.push_back({s->trees[r.t].lde_ptr(r.g), sampled[r.t][r.g][pi]});
       }
     }
-    std::vector<QBatchDev> qb(hb.size()); std::vector<QEntryDev> qe;
-    for (size_t b = 0; b < hb.size(); ++b) {
-      QBatchDev& B = qb[b];
-      const qpoint& p = hb[b].p;
-      B.prx[0] = p.x.c[0]; B.prx[1] = p.x.c[1]; B.pix[0] = p.x.c[2]; B.pix[1] = p.x.c[3];
-      B.pry[0] = p.y.c[0]; B.pry[1] = p.y.c[1]; B.piy[0] = p.y.c[2]; B.piy[1] = p.y.c[3];
-      qm31 alpha = qm31_one(), sa = qm31_zero(), sb = qm31_zero();
-      B.first = (u32)qe.size(); B.count = (u32)hb[b].cols.size();
-      for (auto& cv : hb[b].cols) {
-        alpha = qm31_mul(alpha, q_coeff);
-        // complex_conjugate_line_coeffs
-        qm31 a = qm31_sub(qm31_conj(cv.second), cv.second);
-        qm31 c = qm31_sub(qm31_conj(p.y), p.y);
-        qm31 bq = qm31_sub(qm31_mul(cv.second, c), qm31_mul(a, p.y));
-        sa = qm31_add(sa, qm31_mul(alpha, a)); sb = qm31_add(sb, qm31_mul(alpha, bq));
-        qm31 ac = qm31_mul(alpha, c);
-        QEntryDev e; e.col = s->trees[all[cv.first].t].lde_ptr(all[cv.first].g); memcpy(e.c, ac.c, 16); e.pad[0] = e.pad[1] = 0;
-        qe.push_back(e);
-      }
-      memcpy(B.A, sa.c, 16); memcpy(B.B, sb.c, 16);
-      qm31 bc = qm31_pow(q_coeff, hb[b].cols.size());
-      memcpy(B.coeff, bc.c, 16);
-    }
-    ColsGuard dom(ctx);
-    nb200_status st = nb200_cols_alloc(ctx, 2, lg, &dom.c);
-    if (st == NB200_OK) st = domain_points(ctx, lg, dom.c->col(0), dom.c->col(1));
     nb200_cols* q = nullptr;
-    if (st == NB200_OK) st = nb200_cols_alloc(ctx, 4, lg, &q);
-    if (st == NB200_OK) { quotients.push_back(q); qlogs.push_back(lg); st = quotients_launch(ctx, qb.data(), qb.size(), qe.data(), qe.size(), dom.c->col(0), dom.c->col(1), lg, q->d); }
+    nb200_status st = nb200_cols_alloc(ctx, 4, lg, &q);
+    if (st == NB200_OK) { quotients.push_back(q); qlogs.push_back(lg); st = accumulate_quotients(ctx, lg, hb, q_coeff, q->d); }
     if (st != NB200_OK) { free_q(); dfree(ctx, d_params); return st; }
     i = j;
   }
@@ -721,6 +744,83 @@ nb200_status nb200_prove(nb200_scheme* s, const nb200_air* air, const uint32_t* 
   memcpy(o, bytes.data(), bytes.size());
   *proof_out = o; *proof_len = bytes.size();
   return NB200_OK;
+}
+
+// ---- backend-trait level operations (the per-trait surface a `CudaBackend` shim binds; the coarse nb200_prove runs the same code) ----
+static bool secure4(const nb200_cols* c, u32 log) { return c && c->n_cols == 4 && c->log_size == log; }
+
+nb200_status nb200_fold_line(nb200_ctx* ctx, const nb200_cols* src, const uint32_t alpha[4], nb200_cols** dst_out) {
+  if (!ctx || !src || !alpha || !dst_out) return NB200_ERR_ARG;
+  NB_ARG(ctx, src->n_cols == 4 && src->log_size >= 1, "fold_line: src must be a secure column (4 coordinate columns) of at least 2 values");
+  NB_TRY(twiddles_prepare(ctx, src->log_size + 1));
+  nb200_cols* d = nullptr;
+  NB_TRY(nb200_cols_alloc(ctx, 4, src->log_size - 1, &d));
+  qm31 a; memcpy(a.c, alpha, 16);
+  nb200_status st = fold_line(ctx, d->d, src->d, src->log_size, a);
+  if (st != NB200_OK) { nb200_cols_free(ctx, d); return st; }
+  *dst_out = d;
+  return NB200_OK;
+}
+nb200_status nb200_fold_circle_into_line(nb200_ctx* ctx, nb200_cols* dst, const nb200_cols* src, const uint32_t alpha[4]) {
+  if (!ctx || !dst || !src || !alpha) return NB200_ERR_ARG;
+  NB_ARG(ctx, src->n_cols == 4 && src->log_size >= 3 && secure4(dst, src->log_size - 1), "fold_circle_into_line: src = 4 columns of 2^k (k >= 3), dst = 4 columns of 2^(k-1)");
+  NB_TRY(twiddles_prepare(ctx, src->log_size));
+  qm31 a; memcpy(a.c, alpha, 16);
+  return fold_circle_into_line(ctx, dst->d, src->d, src->log_size, a);
+}
+nb200_status nb200_accumulate(nb200_ctx* ctx, nb200_cols* a, const nb200_cols* b) {
+  if (!ctx || !a || !b) return NB200_ERR_ARG;
+  NB_ARG(ctx, a->n_cols == b->n_cols && a->log_size == b->log_size, "accumulate: shape mismatch");
+  return add_inplace(ctx, a->d, b->d, a->n_cols << a->log_size);
+}
+nb200_status nb200_grind(nb200_ctx* ctx, const uint8_t digest[32], uint32_t pow_bits, uint64_t* nonce_out) {
+  if (!ctx || !digest || !nonce_out) return NB200_ERR_ARG;
+  return grind(ctx, digest, pow_bits, nonce_out);
+}
+nb200_status nb200_fri_quotients(nb200_ctx* ctx, const nb200_cols* const* batches, size_t n_batches, uint32_t log_size,
+                                 const nb200_sample_batch* sample_batches, size_t n_sample_batches,
+                                 const nb200_sample_entry* entries, size_t n_entries, const uint32_t random_coeff[4], nb200_cols** out) {
+  if (!ctx || (!batches && n_batches) || (!sample_batches && n_sample_batches) || (!entries && n_entries) || !random_coeff || !out) return NB200_ERR_ARG;
+  std::vector<const u32*> cols;
+  for (size_t b = 0; b < n_batches; ++b) {
+    NB_ARG(ctx, batches[b] && batches[b]->log_size == log_size, "fri_quotients: every column must have 2^log_size rows");
+    for (size_t c = 0; c < batches[b]->n_cols; ++c) cols.push_back(batches[b]->col(c));
+  }
+  std::vector<SampleBatch> hb(n_sample_batches);
+  for (size_t b = 0; b < n_sample_batches; ++b) {
+    const nb200_sample_batch& sb = sample_batches[b];
+    NB_ARG(ctx, sb.first_entry <= n_entries && sb.n_entries <= n_entries - sb.first_entry, "fri_quotients: sample batch entry range");
+    memcpy(hb[b].p.x.c, sb.point, 16); memcpy(hb[b].p.y.c, sb.point + 4, 16);
+    for (size_t e = sb.first_entry; e < sb.first_entry + sb.n_entries; ++e) {
+      NB_ARG(ctx, entries[e].column < cols.size(), "fri_quotients: column index out of range");
+      qm31 v; memcpy(v.c, entries[e].value, 16);
+      hb[b].cols.push_back({cols[entries[e].column], v});
+    }
+  }
+  qm31 rc; memcpy(rc.c, random_coeff, 16);
+  nb200_cols* q = nullptr;
+  NB_TRY(nb200_cols_alloc(ctx, 4, log_size, &q));
+  nb200_status st = accumulate_quotients(ctx, log_size, hb, rc, q->d);
+  if (st != NB200_OK) { nb200_cols_free(ctx, q); return st; }
+  *out = q;
+  return NB200_OK;
+}
+nb200_status nb200_constraint_quotients(nb200_scheme* s, const nb200_air* air, uint32_t component, const uint32_t* params, size_t n_params,
+                                        const uint32_t* coeffs, size_t n_coeffs, nb200_cols* accum) {
+  if (!s || !air || !accum || (!coeffs && n_coeffs)) return NB200_ERR_ARG;
+  nb200_ctx* ctx = s->ctx;
+  NB_ARG(ctx, n_params == air->prog.n_params, "constraint quotients: parameter table size");
+  std::vector<qm31> cf(n_coeffs);
+  if (n_coeffs) memcpy(cf.data(), coeffs, n_coeffs * 16);
+  u32* d_params = nullptr;
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(n_params, 1) * 16));
+  nb200_status st = NB200_OK;
+  if (n_params && cudaMemcpyAsync(d_params, params, n_params * 16, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "h2d");
+  if (st == NB200_OK) st = component_quotients(s, const_cast<nb200_air*>(air), component, d_params, cf, accum);
+  // params is caller memory: make sure the copy has been consumed before returning
+  if (st == NB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "sync");
+  dfree(ctx, d_params);
+  return st;
 }
 
 }  // extern "C"

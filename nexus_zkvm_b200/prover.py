@@ -166,6 +166,13 @@ class CommitmentSchemeProver:
         # `inter` holds device batches straight from gen_interaction: no host round trip
         return self.commit_batches(list(inter), ch)
 
+    def constraint_quotients(self, comp, params, coeffs, accum):
+        """ComponentProver::evaluate_constraint_quotients_on_domain for one component: accum (4-column batch) += quotients."""
+        p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
+        cf = np.ascontiguousarray(np.array(coeffs, dtype=np.uint32).reshape(-1, 4))
+        self.ctx._chk(lib().nb200_constraint_quotients(self._h, self.air._h, C.c_uint32(comp), p.ctypes.data_as(u32p), C.c_size_t(p.shape[0]),
+                                                       cf.ctypes.data_as(u32p), C.c_size_t(cf.shape[0]), accum._h))
+
     def prove(self, ch, params):
         p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
         out = u8p(); ln = C.c_size_t()
@@ -173,6 +180,61 @@ class CommitmentSchemeProver:
         data = bytes(np.ctypeslib.as_array(out, shape=(max(ln.value, 1),))[:ln.value])
         lib().nb200_free(C.cast(out, C.c_void_p))
         return data
+
+
+class SampleBatch(C.Structure):
+    _fields_ = [("point", C.c_uint32 * 8), ("first_entry", C.c_size_t), ("n_entries", C.c_size_t)]
+
+
+class SampleEntry(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("value", C.c_uint32 * 4)]
+
+
+def _q(v):
+    return (C.c_uint32 * 4)(*[int(x) for x in np.asarray(v, dtype=np.uint32).reshape(4)])
+
+
+def fold_line(ctx, src, alpha):
+    """FriOps::fold_line on a secure column (4-column batch) -> new batch of half the length."""
+    out = C.c_void_p()
+    ctx._chk(lib().nb200_fold_line(ctx._h, src._h, _q(alpha), C.byref(out)))
+    return Columns(ctx, out)
+
+
+def fold_circle_into_line(ctx, dst, src, alpha):
+    """FriOps::fold_circle_into_line: dst = dst * alpha^2 + fold(src) (in place)."""
+    ctx._chk(lib().nb200_fold_circle_into_line(ctx._h, dst._h, src._h, _q(alpha)))
+
+
+def accumulate(ctx, a, b):
+    """AccumulationOps::accumulate: a += b."""
+    ctx._chk(lib().nb200_accumulate(ctx._h, a._h, b._h))
+
+
+def grind(ctx, digest, pow_bits):
+    """GrindOps::grind."""
+    nonce = C.c_uint64()
+    ctx._chk(lib().nb200_grind(ctx._h, (C.c_uint8 * 32).from_buffer_copy(digest), C.c_uint32(pow_bits), C.byref(nonce)))
+    return int(nonce.value)
+
+
+def fri_quotients(ctx, batches, log_size, sample_batches, random_coeff):
+    """QuotientOps::accumulate_quotients.  batches: device column batches (columns numbered through them);
+    sample_batches: [(point8, [(column, value4), ...]), ...] -> new secure column (4 x 2^log_size)."""
+    arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    n_e = sum(len(e) for _p, e in sample_batches)
+    sb = (SampleBatch * max(len(sample_batches), 1))()
+    se = (SampleEntry * max(n_e, 1))()
+    k = 0
+    for i, (pt, ents) in enumerate(sample_batches):
+        sb[i].point = (C.c_uint32 * 8)(*[int(x) for x in np.asarray(pt, dtype=np.uint32).reshape(8)])
+        sb[i].first_entry, sb[i].n_entries = k, len(ents)
+        for ci, v in ents:
+            se[k].column = int(ci); se[k].value = _q(v); k += 1
+    out = C.c_void_p()
+    ctx._chk(lib().nb200_fri_quotients(ctx._h, arr, C.c_size_t(len(batches)), C.c_uint32(log_size), sb, C.c_size_t(len(sample_batches)),
+                                       se, C.c_size_t(n_e), _q(random_coeff), C.byref(out)))
+    return Columns(ctx, out)
 
 
 class CudaBackend:

@@ -306,4 +306,76 @@ int orc_verify(const uint32_t* air_words, size_t n_air, const uint32_t* params, 
 
 void* orc_channel_clone(void* c) { return new Channel(*(Channel*)c); }
 
+// ---- backend-trait level operations (FriOps / QuotientOps / AccumulationOps / GrindOps / ComponentProver), used by the
+// op-level parity tests of the C ABI.  Secure columns travel as 4 coordinate columns: buf[k * n + i].
+namespace {
+SecureCol read_secure(const uint32_t* buf, size_t n) { SecureCol s; s.resize(n); for (int k = 0; k < 4; ++k) for (size_t i = 0; i < n; ++i) s.c[k][i] = M31::raw(buf[k * n + i]); return s; }
+void write_secure(const SecureCol& s, uint32_t* buf) { size_t n = s.size(); for (int k = 0; k < 4; ++k) for (size_t i = 0; i < n; ++i) buf[k * n + i] = s.c[k][i].v; }
+QM31 read_q(const uint32_t* p) { return QM31::from_u32(p[0], p[1], p[2], p[3]); }
+}
+
+// FriOps::fold_line on LineDomain(Coset::half_odds(log_size)) (the domain FriProver::commit walks)
+void orc_fold_line(uint32_t log_size, const uint32_t* src, const uint32_t alpha[4], uint32_t* dst) {
+  size_t n = (size_t)1 << log_size;
+  SecureCol s = read_secure(src, n);
+  LineEval e; e.domain = LineDomain(Coset::half_odds(log_size)); e.values.resize(n);
+  for (size_t i = 0; i < n; ++i) e.values[i] = s.at(i);
+  LineEval o = fold_line(e, read_q(alpha));
+  write_secure(to_secure_col(o.values), dst);
+}
+
+// FriOps::fold_circle_into_line: dst (2^(src_log-1) values, in/out) = dst * alpha^2 + fold(src)
+void orc_fold_circle_into_line(uint32_t src_log, uint32_t* dst, const uint32_t* src, const uint32_t alpha[4]) {
+  size_t n = (size_t)1 << src_log;
+  SecureCol s = read_secure(src, n), d = read_secure(dst, n / 2);
+  LineEval e; e.domain = LineDomain(Coset::half_odds(src_log - 1)); e.values.resize(n / 2);
+  for (size_t i = 0; i < n / 2; ++i) e.values[i] = d.at(i);
+  fold_circle_into_line(e, s, src_log, read_q(alpha));
+  write_secure(to_secure_col(e.values), dst);
+}
+
+// QuotientOps::accumulate_quotients; batch b covers entries [first[b], first[b] + count[b]); entry = (column index, sampled value)
+void orc_accumulate_quotients(uint32_t log_size, size_t n_cols, const uint32_t* const* cols, const uint32_t random_coeff[4],
+                              size_t n_batches, const uint32_t* points /*8 per batch: x[4], y[4]*/, const uint64_t* first, const uint64_t* count,
+                              const uint32_t* entry_cols, const uint32_t* entry_values /*4 per entry*/, uint32_t* out) {
+  size_t n = (size_t)1 << log_size;
+  std::vector<Col> c(n_cols);
+  for (size_t k = 0; k < n_cols; ++k) { c[k].resize(n); for (size_t i = 0; i < n; ++i) c[k][i] = M31::raw(cols[k][i]); }
+  std::vector<const Col*> cp; for (auto& x : c) cp.push_back(&x);
+  std::vector<ColumnSampleBatch> batches(n_batches);
+  for (size_t b = 0; b < n_batches; ++b) {
+    batches[b].point = CirclePoint<QM31>{read_q(points + 8 * b), read_q(points + 8 * b + 4)};
+    for (uint64_t e = first[b]; e < first[b] + count[b]; ++e) batches[b].cols.push_back({(size_t)entry_cols[e], read_q(entry_values + 4 * e)});
+  }
+  write_secure(accumulate_quotients(log_size, cp, read_q(random_coeff), batches), out);
+}
+
+// GrindOps::grind on a channel whose digest is `digest`
+uint64_t orc_grind(const uint8_t digest[32], uint32_t pow_bits) {
+  Channel ch; memcpy(ch.digest.data(), digest, 32);
+  return grind(ch, pow_bits);
+}
+
+// ComponentProver::evaluate_constraint_quotients_on_domain for component `comp` over the prover's committed trees:
+// accum (4 coordinate columns of 2^eval_log, in/out) += quotients
+int orc_prover_constraint_quotients(void* pp, uint32_t comp, const uint32_t* params, size_t n_params, const uint32_t* coeffs /*4 per constraint*/, uint32_t* accum) {
+  try {
+    OrcProver* p = (OrcProver*)pp;
+    const Component& c = p->air.comps.at(comp);
+    size_t en = (size_t)1 << c.eval_log();
+    SecureCol acc = read_secure(accum, en);
+    std::vector<QM31> coeff(c.n_constraints);
+    for (uint32_t k = 0; k < c.n_constraints; ++k) coeff[k] = read_q(coeffs + 4 * k);
+    component_quotients(c, p->trees, read_params(params, n_params), coeff, acc);
+    write_secure(acc, accum);
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// ColumnOps::bit_reverse_column
+void orc_bit_reverse_column(uint32_t* col, uint32_t log_size) {
+  size_t n = (size_t)1 << log_size;
+  for (size_t i = 0; i < n; ++i) { size_t j = bit_reverse_index(i, log_size); if (i < j) std::swap(col[i], col[j]); }
+}
+
 }  // extern "C"

@@ -256,6 +256,43 @@ inline std::pair<std::vector<Col>, QM31> gen_interaction_trace(const Component& 
 // composition polynomial (prover/air/{component_prover,accumulation}.rs + constraint-framework component.rs)
 inline std::vector<QM31> secure_powers(QM31 x, size_t n) { std::vector<QM31> p(n); QM31 a = QM31::one(); for (size_t i = 0; i < n; ++i) { p[i] = a; a = a * x; } return p; }
 
+// ComponentProver::evaluate_constraint_quotients_on_domain for one component: acc[row] += (sum_k coeff[k] * constraint_k(row)) / vanishing(row)
+// on CanonicCoset(eval_log).circle_domain() (bit-reversed); `coeff` are the random-coefficient powers assigned to this component.
+inline void component_quotients(const Component& c, const std::vector<Tree>& trees, const std::vector<QM31>& params, const std::vector<QM31>& coeff, SecureCol& acc) {
+  uint32_t elog = c.eval_log();
+  size_t en = (size_t)1 << elog;
+  CircleDomain eval_domain = CanonicCoset(elog).circle_domain();
+  // evaluate every referenced column on the eval domain
+  std::map<std::pair<uint32_t, uint32_t>, Col> ext;
+  for (auto& m : c.masks) {
+    auto key = std::make_pair(m.tree, m.col);
+    if (!ext.count(key)) ext[key] = evaluate_col(trees.at(m.tree).polys.at(m.col), elog);
+  }
+  std::vector<const Col*> mcol(c.masks.size());
+  for (size_t m = 0; m < c.masks.size(); ++m) mcol[m] = &ext[{c.masks[m].tree, c.masks[m].col}];
+  // denominators: coset_vanishing(trace coset, eval_domain.at(i)) for i < 2^log_expand, bit reversed, inverted
+  Coset trace_coset = CanonicCoset(c.log_size).coset;
+  std::vector<M31> dinv((size_t)1 << c.log_expand);
+  for (size_t i = 0; i < dinv.size(); ++i) dinv[i] = inv(coset_vanishing<M31>(trace_coset, eval_domain.at(i)));
+  bit_reverse(dinv);
+#pragma omp parallel
+  {
+    std::vector<M31> mask(c.masks.size());
+    std::vector<M31> br(c.n_base_regs); std::vector<QM31> er(c.n_ext_regs);
+#pragma omp for schedule(static)
+    for (size_t row = 0; row < en; ++row) {
+      for (size_t m = 0; m < c.masks.size(); ++m) {
+        size_t r = c.masks[m].off == 0 ? row : offset_bit_reversed_circle_domain_index(row, c.log_size, elog, c.masks[m].off);
+        mask[m] = (*mcol[m])[r];
+      }
+      QM31 row_res = QM31::zero(); size_t k = 0;
+      run_program<M31>(c.prog, mask.data(), params, br, er, [&](QM31 v) { row_res = row_res + coeff[k] * v; ++k; }, [](QM31, QM31) {});
+      M31 di = dinv[row >> c.log_size];
+      acc.set(row, acc.at(row) + row_res * di);
+    }
+  }
+}
+
 inline std::array<Col, 4> compute_composition(const Air& air, const std::vector<Tree>& trees, const std::vector<QM31>& params, QM31 random_coeff) {
   size_t n_total = 0; uint32_t max_log = 0;
   for (auto& c : air.comps) { n_total += c.n_constraints; max_log = std::max(max_log, c.eval_log()); }
@@ -264,43 +301,12 @@ inline std::array<Col, 4> compute_composition(const Air& air, const std::vector<
   size_t g0 = 0;
   for (const Component& c : air.comps) {
     uint32_t elog = c.eval_log();
-    size_t en = (size_t)1 << elog;
-    CircleDomain eval_domain = CanonicCoset(elog).circle_domain();
-    // evaluate every referenced column on the eval domain
-    std::map<std::pair<uint32_t, uint32_t>, Col> ext;
-    for (auto& m : c.masks) {
-      auto key = std::make_pair(m.tree, m.col);
-      if (!ext.count(key)) ext[key] = evaluate_col(trees.at(m.tree).polys.at(m.col), elog);
-    }
-    std::vector<const Col*> mcol(c.masks.size());
-    for (size_t m = 0; m < c.masks.size(); ++m) mcol[m] = &ext[{c.masks[m].tree, c.masks[m].col}];
-    // denominators: coset_vanishing(trace coset, eval_domain.at(i)) for i < 2^log_expand, bit reversed, inverted
-    Coset trace_coset = CanonicCoset(c.log_size).coset;
-    std::vector<M31> dinv((size_t)1 << c.log_expand);
-    for (size_t i = 0; i < dinv.size(); ++i) dinv[i] = inv(coset_vanishing<M31>(trace_coset, eval_domain.at(i)));
-    bit_reverse(dinv);
     // this component's coefficients: the last n_constraints of the remaining powers, reversed
     std::vector<QM31> coeff(c.n_constraints);
     for (uint32_t k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
     g0 += c.n_constraints;
-    if (!sub[elog]) { sub[elog] = std::make_unique<SecureCol>(); sub[elog]->resize(en); }
-    SecureCol& acc = *sub[elog];
-#pragma omp parallel
-    {
-      std::vector<M31> mask(c.masks.size());
-      std::vector<M31> br(c.n_base_regs); std::vector<QM31> er(c.n_ext_regs);
-#pragma omp for schedule(static)
-      for (size_t row = 0; row < en; ++row) {
-        for (size_t m = 0; m < c.masks.size(); ++m) {
-          size_t r = c.masks[m].off == 0 ? row : offset_bit_reversed_circle_domain_index(row, c.log_size, elog, c.masks[m].off);
-          mask[m] = (*mcol[m])[r];
-        }
-        QM31 row_res = QM31::zero(); size_t k = 0;
-        run_program<M31>(c.prog, mask.data(), params, br, er, [&](QM31 v) { row_res = row_res + coeff[k] * v; ++k; }, [](QM31, QM31) {});
-        M31 di = dinv[row >> c.log_size];
-        acc.set(row, acc.at(row) + row_res * di);
-      }
-    }
+    if (!sub[elog]) { sub[elog] = std::make_unique<SecureCol>(); sub[elog]->resize((size_t)1 << elog); }
+    component_quotients(c, trees, params, coeff, *sub[elog]);
   }
   // DomainEvaluationAccumulator::finalize
   std::array<Col, 4> cur; bool have = false;

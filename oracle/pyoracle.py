@@ -305,6 +305,66 @@ class Prover:
             raise OracleError(f"prove failed ({st}): {last_error()}")
         return bytes(buf[:ln.value])
 
+    def constraint_quotients(self, comp, eval_log, params, coeffs, accum=None):
+        """ComponentProver::evaluate_constraint_quotients_on_domain for one component; returns accum (4 x 2^eval_log) + quotients."""
+        params = np.ascontiguousarray(params, dtype=np.uint32).reshape(-1, 4)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint32).reshape(-1, 4)
+        acc = np.zeros((4, 1 << eval_log), np.uint32) if accum is None else np.ascontiguousarray(accum, dtype=np.uint32).copy()
+        st = lib().orc_prover_constraint_quotients(self._h, C.c_uint32(comp), params.ctypes.data_as(u32p), C.c_size_t(params.shape[0]),
+                                                   coeffs.ctypes.data_as(u32p), acc.ctypes.data_as(u32p))
+        if st:
+            raise OracleError(last_error())
+        return acc
+
+
+def fold_line(src, alpha):
+    """FriOps::fold_line; src = 4 x 2^k coordinate columns on LineDomain(Coset::half_odds(k))."""
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    k = src.shape[1].bit_length() - 1
+    out = np.zeros((4, src.shape[1] // 2), np.uint32)
+    lib().orc_fold_line(C.c_uint32(k), src.ctypes.data_as(u32p), _u32(alpha)[1], out.ctypes.data_as(u32p))
+    return out
+
+
+def fold_circle_into_line(dst, src, alpha):
+    """FriOps::fold_circle_into_line; returns the new dst (dst * alpha^2 + fold(src))."""
+    src = np.ascontiguousarray(src, dtype=np.uint32)
+    out = np.ascontiguousarray(dst, dtype=np.uint32).copy()
+    k = src.shape[1].bit_length() - 1
+    lib().orc_fold_circle_into_line(C.c_uint32(k), out.ctypes.data_as(u32p), src.ctypes.data_as(u32p), _u32(alpha)[1])
+    return out
+
+
+def accumulate_quotients(cols, random_coeff, batches):
+    """QuotientOps::accumulate_quotients.  cols: equal-length columns; batches: [(point8, [(col_index, value4), ...]), ...]."""
+    cols, arr, logs = _col_ptrs(cols)
+    log_size = int(logs[0])
+    pts = np.ascontiguousarray([b[0] for b in batches], dtype=np.uint32).reshape(-1, 8)
+    first, count, ecols, evals = [], [], [], []
+    for _pt, ents in batches:
+        first.append(len(ecols)); count.append(len(ents))
+        for ci, v in ents:
+            ecols.append(ci); evals.append(v)
+    first = np.array(first, np.uint64); count = np.array(count, np.uint64)
+    ecols = np.array(ecols, np.uint32); evals = np.ascontiguousarray(evals, dtype=np.uint32).reshape(-1, 4)
+    out = np.zeros((4, 1 << log_size), np.uint32)
+    u64p = C.POINTER(C.c_uint64)
+    lib().orc_accumulate_quotients(C.c_uint32(log_size), C.c_size_t(len(cols)), arr, _u32(random_coeff)[1],
+                                   C.c_size_t(len(batches)), pts.ctypes.data_as(u32p), first.ctypes.data_as(u64p), count.ctypes.data_as(u64p),
+                                   ecols.ctypes.data_as(u32p), evals.ctypes.data_as(u32p), out.ctypes.data_as(u32p))
+    return out
+
+
+def grind(digest: bytes, pow_bits):
+    lib().orc_grind.restype = C.c_uint64
+    return int(lib().orc_grind((C.c_uint8 * 32).from_buffer_copy(digest), C.c_uint32(pow_bits)))
+
+
+def bit_reverse_column(col):
+    out = np.ascontiguousarray(col, dtype=np.uint32).copy()
+    lib().orc_bit_reverse_column(out.ctypes.data_as(u32p), C.c_uint32(out.size.bit_length() - 1))
+    return out
+
 
 def verify(air_words, params, proof_bytes, channel, col_logs):
     """col_logs: [tree0 logs, tree1 logs, tree2 logs].  Raises OracleError on rejection."""

@@ -68,3 +68,28 @@ def test_paired_logup_proof_verifies():
     proof, claimed, aux = M.prove(m, OracleBackend(), cols, mult)
     assert M.verify_claimed_sums(claimed)
     verify(m, proof, aux)
+
+
+# ---- backend-trait level oracle functions (the checkers of tests/test_gpu_backend_ops.py) ---------------------------
+def test_oracle_fold_ops_are_linear_and_grind_is_minimal():
+    import hashlib
+    rng = np.random.default_rng(42)
+    P = (1 << 31) - 1
+    a, b = (rng.integers(0, P, size=(4, 64), dtype=np.uint32) for _ in range(2))
+    alpha = rng.integers(0, P, size=4, dtype=np.uint32)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    add = lambda x, y: ((x.astype(np.uint64) + y) % P).astype(np.uint32)
+    assert np.array_equal(orc.fold_line(s, alpha), add(orc.fold_line(a, alpha), orc.fold_line(b, alpha)))
+    z = np.zeros((4, 32), np.uint32)
+    assert np.array_equal(orc.fold_circle_into_line(z, s, alpha), add(orc.fold_circle_into_line(z, a, alpha), orc.fold_circle_into_line(z, b, alpha)))
+    # folding a constant secure column: f0 = f1 = c -> (c + c) + alpha * 0 = 2c
+    c = np.tile(np.array([[5], [6], [7], [8]], np.uint32), (1, 16))
+    assert np.array_equal(orc.fold_line(c, alpha), np.tile(np.array([[10], [12], [14], [16]], np.uint32), (1, 8)))
+    # grind: the nonce satisfies the predicate and no smaller one does (pow_variant 0: Blake2s(digest || nonce_le))
+    digest = bytes(range(32))
+    def tz(nonce):
+        h = hashlib.blake2s(digest + nonce.to_bytes(8, "little")).digest()
+        v = int.from_bytes(h[:16], "little")
+        return 128 if v == 0 else (v & -v).bit_length() - 1
+    n = orc.grind(digest, 9)
+    assert tz(n) >= 9 and all(tz(k) < 9 for k in range(n))
