@@ -151,6 +151,9 @@ nb200_status nb200_air_load(nb200_ctx*, const uint32_t* words, size_t n_words, n
 void nb200_air_free(nb200_air*);
 uint32_t nb200_air_n_params(const nb200_air*);
 uint32_t nb200_air_n_components(const nb200_air*);
+/* the CUDA C source a component's constraint program is specialised to at first use (NVRTC, sm_100a); malloc'ed,
+ * NUL-terminated, free with nb200_free.  Works without a device (ctx may have been NULL at nb200_air_load). */
+nb200_status nb200_air_kernel_source(const nb200_air*, uint32_t component, char** out);
 
 /* ---- CommitmentSchemeProver<B, Blake2sMerkleChannel> (machine.rs:202-203) ------------------------------ */
 typedef struct nb200_scheme nb200_scheme;

@@ -322,9 +322,14 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
     const u32** d_cols = nullptr;
     NB_CUDA(ctx, dmalloc(ctx, (void**)&d_cols, mask_cols.size() * sizeof(u32*)));
     NB_CUDA(ctx, cudaMemcpyAsync(d_cols, mask_cols.data(), mask_cols.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
-    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_coeff, d_dinv, acc);
+    std::vector<u32> tab;
+    jit_coeff_table(coeffs, tab);
+    u32* d_tab = nullptr;
+    NB_CUDA(ctx, dmalloc(ctx, (void**)&d_tab, tab.size() * 4 + 16));
+    NB_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_tab, d_dinv, acc);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, (void*)d_cols);
+    dfree(ctx, (void*)d_cols); dfree(ctx, d_tab);
   } else {
     InterpArgs a{};
     a.prog = d_prog; a.n_instr = (u32)c.prog.size(); a.masks = d_masks; a.params = d_params;

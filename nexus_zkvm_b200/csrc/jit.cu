@@ -52,23 +52,45 @@ __device__ __forceinline__ u32 mn(u32 a, u32 b) { return a < b ? a : b; }
 __device__ __forceinline__ u32 add(u32 a, u32 b) { u32 s = a + b; return mn(s, s - P31); }
 __device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return mn(d, d + P31); }
 __device__ __forceinline__ u32 neg(u32 a) { return a ? P31 - a : 0u; }
-__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 p = (u64)a * b; u32 s = ((u32)p & P31) + (u32)(p >> 31); return mn(s, s - P31); }
+// one product: a * 2b = hi * 2^32 + lo  =>  a * b = hi * 2^31 + lo / 2 == hi + lo / 2 (mod P), below 2P
+__device__ __forceinline__ u32 mul2(u32 a, u32 b2) { u64 p = (u64)a * (u64)b2; u32 s = (u32)(p >> 32) + ((u32)p >> 1); return mn(s, s - P31); }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { return mul2(a, b + b); }
+// canonical residue of any 64-bit value: 2^32 == 2 and 2^31 == 1 (mod P)
+__device__ __forceinline__ u32 red64(u64 x) {
+  u64 y;                                                // y = 2 * hi + lo < 3 * 2^32 (mad.wide keeps NVVM from expanding it into a carry chain)
+  asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(y) : "r"((u32)(x >> 32)), "l"((u64)(u32)x));
+  u32 yl = (u32)y, yh = (u32)(y >> 32);
+  u32 s = (yl & P31) + __funnelshift_r(yl, yh, 31);     // <= P + 5
+  return mn(s, s - P31);
+}
 __device__ __forceinline__ Q qadd(Q x, Q y) { return Q{add(x.c0, y.c0), add(x.c1, y.c1), add(x.c2, y.c2), add(x.c3, y.c3)}; }
 __device__ __forceinline__ Q qsub(Q x, Q y) { return Q{sub(x.c0, y.c0), sub(x.c1, y.c1), sub(x.c2, y.c2), sub(x.c3, y.c3)}; }
 __device__ __forceinline__ Q qneg(Q x) { return Q{neg(x.c0), neg(x.c1), neg(x.c2), neg(x.c3)}; }
-__device__ __forceinline__ Q qmulb(Q x, u32 b) { return Q{mul(x.c0, b), mul(x.c1, b), mul(x.c2, b), mul(x.c3, b)}; }
+__device__ __forceinline__ Q qmulb(Q x, u32 b) { u32 b2 = b + b; return Q{mul2(x.c0, b2), mul2(x.c1, b2), mul2(x.c2, b2), mul2(x.c3, b2)}; }
 __device__ __forceinline__ Q qaddb(Q x, u32 b) { x.c0 = add(x.c0, b); return x; }
 __device__ __forceinline__ Q qsubb(Q x, u32 b) { x.c0 = sub(x.c0, b); return x; }
-__device__ __noinline__ Q qmul(Q x, Q y) {
-  // (a + bu)(c + du) = (ac + R bd) + (ad + bc)u,  R = 2 + i   (same formula as m31.cuh qm31_mul)
-  u32 ac0 = sub(mul(x.c0, y.c0), mul(x.c1, y.c1)), ac1 = add(mul(x.c0, y.c1), mul(x.c1, y.c0));
-  u32 bd0 = sub(mul(x.c2, y.c2), mul(x.c3, y.c3)), bd1 = add(mul(x.c2, y.c3), mul(x.c3, y.c2));
-  u32 r0 = sub(add(bd0, bd0), bd1), r1 = add(bd0, add(bd1, bd1));
-  u32 ad0 = sub(mul(x.c0, y.c2), mul(x.c1, y.c3)), ad1 = add(mul(x.c0, y.c3), mul(x.c1, y.c2));
-  u32 bc0 = sub(mul(x.c2, y.c0), mul(x.c3, y.c1)), bc1 = add(mul(x.c2, y.c1), mul(x.c3, y.c0));
-  return Q{add(ac0, r0), add(ac1, r1), add(ad0, bc0), add(ad1, bc1)};
+// acc + x * y in QM31 with every coordinate accumulated in 64 bits and reduced once.  (a + bu)(c + du) = (ac + R bd) + (ad + bc)u,
+// R = 2 + i (the formula of m31.cuh qm31_mul), regrouped per coordinate of x so that each output is four products:
+//   r0 = x0 y0 - x1 y1 + x2 (2 y2 - y3) - x3 (y2 + 2 y3)      r1 = x0 y1 + x1 y0 + x2 (y2 + 2 y3) + x3 (2 y2 - y3)
+//   r2 = x0 y2 - x1 y3 + x2 y0 - x3 y1                        r3 = x0 y3 + x1 y2 + x2 y1 + x3 y0
+// ny1 = P - y1, ny3 = P - y3, g = 2 y2 - y3, gp = y2 + 2 y3, h = P - gp: all <= P, so 4 products + acc < 2^64.
+__device__ __forceinline__ Q qmac(Q acc, Q x, u32 y0, u32 y1, u32 y2, u32 y3, u32 ny1, u32 ny3, u32 g, u32 gp, u32 h) {
+  u64 r0 = (u64)acc.c0 + (u64)x.c0 * y0 + (u64)x.c1 * ny1 + (u64)x.c2 * g + (u64)x.c3 * h;
+  u64 r1 = (u64)acc.c1 + (u64)x.c0 * y1 + (u64)x.c1 * y0 + (u64)x.c2 * gp + (u64)x.c3 * g;
+  u64 r2 = (u64)acc.c2 + (u64)x.c0 * y2 + (u64)x.c1 * ny3 + (u64)x.c2 * y0 + (u64)x.c3 * ny1;
+  u64 r3 = (u64)acc.c3 + (u64)x.c0 * y3 + (u64)x.c1 * y2 + (u64)x.c2 * y1 + (u64)x.c3 * y0;
+  return Q{red64(r0), red64(r1), red64(r2), red64(r3)};
 }
-__device__ __forceinline__ Q ldq(const u32* p) { return Q{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}; }
+__device__ __forceinline__ Q qmul(Q x, Q y) {
+  u32 gp = add(add(y.c3, y.c3), y.c2), g = sub(add(y.c2, y.c2), y.c3);
+  return qmac(Q{0u, 0u, 0u, 0u}, x, y.c0, y.c1, y.c2, y.c3, P31 - y.c1, P31 - y.c3, g, gp, P31 - gp);
+}
+__device__ __forceinline__ Q ldq(const u32* p) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); return Q{v.x, v.y, v.z, v.w}; }
+// rr + coeff * x with the coefficient's derived multipliers precomputed by the host (12 words per constraint, see jit_coeff_table)
+__device__ __forceinline__ Q qmac_tab(Q acc, Q x, const u32* t) {
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(t)), b = __ldg(reinterpret_cast<const uint4*>(t) + 1), c = __ldg(reinterpret_cast<const uint4*>(t) + 2);
+  return qmac(acc, x, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x);
+}
 )SRC";
 
 std::string gen_source(const AirComponent& c) {
@@ -89,7 +111,8 @@ std::string gen_source(const AirComponent& c) {
     else s << "__ldg(cols[" << m << "] + offrow(row, " << c.masks[m].off << "))";
     return s.str();
   };
-  const size_t CH = 250;
+  size_t CH = 250;
+  if (const char* e = getenv("NB200_JIT_CHUNK")) { long v = atol(e); if (v >= 16 && v <= 100000) CH = (size_t)v; }
   size_t n_chunks = (c.prog.size() + CH - 1) / CH;
   u32 k = 0;
   for (size_t ci = 0; ci < n_chunks; ++ci) {
@@ -116,25 +139,30 @@ std::string gen_source(const AirComponent& c) {
         case OP_MULEB: o << "e[" << in.dst << "] = qmulb(e[" << in.a << "], b[" << in.b << "]);"; break;
         case OP_BTOE: o << "e[" << in.dst << "] = Q{b[" << in.a << "], 0u, 0u, 0u};"; break;
         case OP_LOADME: o << "e[" << in.dst << "] = Q{" << ld(in.a) << ", " << ld(in.a + 1) << ", " << ld(in.a + 2) << ", " << ld(in.a + 3) << "};"; break;
-        case OP_CONSTRB: o << "rr = qadd(rr, qmulb(ldq(coeff + " << 4 * k << "), b[" << in.a << "]));"; ++k; break;
-        case OP_CONSTRE: o << "rr = qadd(rr, qmul(ldq(coeff + " << 4 * k << "), e[" << in.a << "]));"; ++k; break;
+        case OP_CONSTRB: o << "rr = qadd(rr, qmulb(ldq(coeff + " << JIT_COEFF_WORDS * k << "), b[" << in.a << "]));"; ++k; break;
+        case OP_CONSTRE: o << "rr = qmac_tab(rr, e[" << in.a << "], coeff + " << JIT_COEFF_WORDS * k << ");"; ++k; break;
         default: break;
       }
       o << "\n";
     }
     o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.rr = rr;\n}\n";
   }
-  o << "extern \"C\" __global__ void __launch_bounds__(128) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
+  // One CTA of JIT_BLOCK threads per SM, re-converged after every chunk: all warps of an SM then execute the same few tens
+  // of KB of straight-line code at a time, so the instruction cache serves them from one fetch (without the barriers the
+  // warps drift apart over the ~0.5 MB program and the kernel is instruction-fetch bound: stall_no_instruction 11 per issue).
+  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
     << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3) {\n"
-    << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
+    << "  const u32 row = blockIdx.x * " << JIT_BLOCK << " + threadIdx.x;\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
-  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row);\n";
+  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row);\n  __syncthreads();\n";
   o << "  const u32 di = __ldg(dinv + (row >> " << DL << "));\n"
     << "  a0[row] = add(a0[row], mul(s.rr.c0, di)); a1[row] = add(a1[row], mul(s.rr.c1, di));\n"
     << "  a2[row] = add(a2[row], mul(s.rr.c2, di)); a3[row] = add(a3[row], mul(s.rr.c3, di));\n}\n";
   return o.str();
 }
 }  // namespace
+
+std::string jit_source(const AirComponent& c) { return gen_source(c); }
 
 bool jit_enabled() {
   const char* e = getenv("NB200_JIT");
@@ -151,7 +179,7 @@ nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitK
   out->lib = nullptr; out->kernel = nullptr; out->tried = true;
   Nvrtc& n = nvrtc();
   if (!n.ok) return set_err(ctx, NB200_ERR_STATE, "jit: libnvrtc not available");
-  if (c.eval_log() < 7) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");  // grid must be a whole number of 128-thread blocks
+  if (((size_t)1 << c.eval_log()) < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");  // grid must be a whole number of blocks
   std::string src = gen_source(c);
   nvrtcProgram prog;
   if (n.CreateProgram(&prog, src.c_str(), "nb200_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return set_err(ctx, NB200_ERR_STATE, "jit: nvrtcCreateProgram failed");
@@ -177,11 +205,23 @@ nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitK
   return NB200_OK;
 }
 
+// per constraint: y0 y1 y2 y3 | P-y1 P-y3 2y2-y3 y2+2y3 | P-(y2+2y3) 0 0 0   (the multipliers of qmac in the generated code)
+void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out) {
+  out.assign(coeffs.size() * JIT_COEFF_WORDS, 0u);
+  for (size_t k = 0; k < coeffs.size(); ++k) {
+    const u32* y = coeffs[k].c;
+    u32* t = &out[k * JIT_COEFF_WORDS];
+    u32 gp = m31_add(m31_add(y[3], y[3]), y[2]), g = m31_sub(m31_add(y[2], y[2]), y[3]);
+    t[0] = y[0]; t[1] = y[1]; t[2] = y[2]; t[3] = y[3];
+    t[4] = P31 - y[1]; t[5] = P31 - y[3]; t[6] = g; t[7] = gp; t[8] = P31 - gp;
+  }
+}
+
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4]) {
   size_t rows = (size_t)1 << jk.eval_log;
   u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
   void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3};
-  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / 128)), dim3(128), args, 0, ctx->stream);
+  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / JIT_BLOCK)), dim3(JIT_BLOCK), args, 0, ctx->stream);
   ctx->launches += 1;
   if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));
   return NB200_OK;

@@ -2,8 +2,13 @@
 #pragma once
 #include "common.cuh"
 #include "air.h"
+#include <string>
+#include <vector>
 
 namespace nb {
+
+static const u32 JIT_BLOCK = 1024;       // threads per CTA of the generated kernel (one CTA per SM)
+static const u32 JIT_COEFF_WORDS = 12;   // words per constraint in the coefficient table the generated kernel reads
 
 struct JitKernel {
   void* lib = nullptr;     // cudaLibrary_t
@@ -13,9 +18,11 @@ struct JitKernel {
 };
 
 bool jit_enabled();
+std::string jit_source(const AirComponent& c);  // the CUDA C the component is specialised to (inspection / offline ptxas checks)
 nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out);
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff,
                                     const u32* d_dinv, u32* const acc[4]);
 void jit_release(JitKernel& jk);
+void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out);
 
 }  // namespace nb

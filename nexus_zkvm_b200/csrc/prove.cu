@@ -269,13 +269,14 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
   if (st == NB200_OK) {
     u32* accp[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
     JitKernel& jk = air_h->jit[comp_idx];
+    trace_mark(ctx, "constraints: extend columns");
     if (!jk.tried) {
       jk.tried = true;
-      if (jit_enabled() && c.prog.size() >= 64) {
-        trace_mark(ctx, "constraints: extend columns");
+      if (c.prog.size() >= 64 && jit_enabled()) {
+        trace_mark(ctx, "jit: load nvrtc (one-time)");
         nb200_status js = jit_compile_constraints(ctx, c, &jk);
         if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
-        trace_mark(ctx, "jit compile (one-time)");
+        trace_mark(ctx, "jit: compile (one-time)");
       }
     }
     st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jk.kernel ? &jk : nullptr);
@@ -698,6 +699,15 @@ nb200_status nb200_air_load(nb200_ctx* ctx, const uint32_t* words, size_t n_word
 void nb200_air_free(nb200_air* a) { delete a; }
 uint32_t nb200_air_n_params(const nb200_air* a) { return a ? a->prog.n_params : 0; }
 uint32_t nb200_air_n_components(const nb200_air* a) { return a ? (uint32_t)a->prog.comps.size() : 0; }
+nb200_status nb200_air_kernel_source(const nb200_air* a, uint32_t component, char** out) {
+  if (!a || !out || component >= a->prog.comps.size()) return NB200_ERR_ARG;
+  std::string src = jit_source(a->prog.comps[component]);
+  char* o = (char*)malloc(src.size() + 1);
+  if (!o) return NB200_ERR_OOM;
+  memcpy(o, src.c_str(), src.size() + 1);
+  *out = o;
+  return NB200_OK;
+}
 
 // ---- CommitmentSchemeProver ----
 nb200_status nb200_scheme_new(nb200_ctx* ctx, uint32_t pow_bits, uint32_t log_blowup, uint32_t log_last_layer_degree_bound, uint32_t n_queries, nb200_scheme** out) {
