@@ -103,9 +103,11 @@ inline void dfree(nb200_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream
 // ---- internal launchers (implemented in the .cu files) ----
 nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log);
 // Circle iFFT in place over a batch (evaluations -> coefficients)
-nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
+// tw_log = log_size + 1 selects the HALF-DOMAIN transform: the domain is the first half (rows [0, 2^log_size) in bit-reversed order) of
+// CanonicCoset(log_size + 1).circle_domain() instead of CanonicCoset(log_size).circle_domain(); 0 = the canonic domain.
+nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size, u32 tw_log = 0);
 // Circle FFT: coefficients (src, log src_log) zero-extended to dst (log dst_log); src may equal dst if logs match
-nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols);
+nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols, u32 tw_log = 0);
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)
 // overlaps the transforms of chunk k.  `host` is n_cols x 2^log_size words (pinned memory for real overlap).

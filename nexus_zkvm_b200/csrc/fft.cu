@@ -39,6 +39,7 @@ struct FftPass {
   u32 cb;             // columns per CTA
   u32 scale;          // multiply outputs by this (interpolate last pass) if apply_scale
   u32 apply_scale;
+  u32 tn;             // log size of the canonic domain whose twiddle arrays are used (= n, or n + 1 for the half-domain transforms)
   u32 ztop;           // forward transforms of zero-extended input: layers >= ztop are copies (= log2 of the source length)
 };
 
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
       if (j >= jlo) {
         const u32 i = lo + b + j - W;
         const u32 hbase = (tile_hi << (L - (b + j - W) - 1)) | (tau_hi << (3 - j));
-        const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw2 + hbase) : (p.tw2 + (p.tw_len - (1u << (n - i))) + hbase);
+        const u32* __restrict__ src = (W == 0 && b + j == 0) ? (p.ctw2 + hbase) : (p.tw2 + (p.tw_len - (1u << (p.tn - i))) + hbase);
         if (j == 0) {
           uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c4 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
           tw[0] = a.x; tw[1] = a.y; tw[2] = a.z; tw[3] = a.w; tw[4] = c4.x; tw[5] = c4.y; tw[6] = c4.z; tw[7] = c4.w;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass p) {
 #pragma unroll
         for (int kk = 0; kk < (8 >> j); ++kk) {
           const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + kk;
-          tw[off] = (i == 0) ? circle_tw(p.tw, p.tw_len, n, hbase + kk) : line_tw(p.tw, p.tw_len, n, i, hbase + kk);
+          tw[off] = (i == 0) ? circle_tw(p.tw, p.tw_len, p.tn, hbase + kk) : line_tw(p.tw, p.tw_len, p.tn, i, hbase + kk);
         }
       }
     }
@@ -511,13 +512,14 @@ static bool launch_fast(nb200_ctx* ctx, const FftPass& p, nb200_status* st) {
 
 template <bool INV>
 static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* src, size_t src_stride, size_t src_len,
-                                u32* dst, size_t dst_stride, size_t n_cols, u32 n, bool scale, u32 ztop = 0xffffffffu) {
+                                u32* dst, size_t dst_stride, size_t n_cols, u32 n, bool scale, u32 ztop = 0xffffffffu, u32 tw_log = 0) {
   FftPass p;
+  p.tn = tw_log ? tw_log : n;
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = src_len;
   p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
   p.tw_len = 1u << ctx->tw.half_log;
   const u32 *cf = nullptr, *ci = nullptr;
-  NB_TRY(circle_tables(ctx, n, &cf, &ci));
+  NB_TRY(circle_tables(ctx, p.tn, &cf, &ci));
   p.ctw2 = INV ? ci : cf;
   p.tw2 = INV ? ctx->tw.d_itw2 : ctx->tw.d_tw2;
   p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
@@ -567,24 +569,26 @@ static nb200_status launch_small(nb200_ctx* ctx, const u32* src, size_t src_stri
 
 static const u32 SMALL_MAX_LOG = 8;
 
-nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* data, size_t n_cols, u32 n) {
+nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* data, size_t n_cols, u32 n, u32 tw_log) {
   if (n_cols == 0) return NB200_OK;
   NB_ARG(ctx, n <= 30, "interpolate: log size too large");
   if (n == 0) {  // constant polynomial: coeff == value
     if (src != data) NB_CUDA(ctx, cudaMemcpyAsync(data, src, n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     return NB200_OK;
   }
-  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= n, "interpolate: twiddles not prepared for this size");
+  const u32 tn = tw_log ? tw_log : n;
+  NB_ARG(ctx, tn == n || (tn == n + 1 && n > SMALL_MAX_LOG), "interpolate: half-domain transforms need tw_log == n + 1 and n > 8");
+  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= tn, "interpolate: twiddles not prepared for this size");
   size_t len = (size_t)1 << n;
   if (n <= SMALL_MAX_LOG) return launch_small<true>(ctx, src, len, len, data, len, n_cols, n, true);
   std::vector<PassPlan> plan;
   plan_passes(n, plan);
   for (size_t k = 0; k < plan.size(); ++k)
-    NB_TRY(launch_pass<true>(ctx, plan[k], k == 0 ? src : data, len, len, data, len, n_cols, n, k + 1 == plan.size()));
+    NB_TRY(launch_pass<true>(ctx, plan[k], k == 0 ? src : data, len, len, data, len, n_cols, n, k + 1 == plan.size(), 0xffffffffu, tn));
   return NB200_OK;
 }
 
-nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 n, size_t n_cols) {
+nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 n, size_t n_cols, u32 tw_log) {
   if (n_cols == 0) return NB200_OK;
   NB_ARG(ctx, src_log <= n && n <= 30, "evaluate: bad sizes");
   size_t slen = (size_t)1 << src_log, len = (size_t)1 << n;
@@ -592,15 +596,17 @@ nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst,
     if (src != dst) NB_CUDA(ctx, cudaMemcpyAsync(dst, src, n_cols * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     return NB200_OK;
   }
-  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= n, "evaluate: twiddles not prepared for this size");
+  const u32 tn = tw_log ? tw_log : n;
+  NB_ARG(ctx, tn == n || (tn == n + 1 && n > SMALL_MAX_LOG), "evaluate: half-domain transforms need tw_log == n + 1 and n > 8");
+  NB_ARG(ctx, ctx->tw.d_tw && ctx->tw.half_log + 1 >= tn, "evaluate: twiddles not prepared for this size");
   NB_ARG(ctx, src != dst || src_log == n, "evaluate: in-place requires equal sizes");
   if (n <= SMALL_MAX_LOG) return launch_small<false>(ctx, src, slen, slen, dst, len, n_cols, n, false);
   std::vector<PassPlan> plan;
   plan_passes(n, plan);
   for (size_t k = plan.size(); k-- > 0;) {
     bool first = (k + 1 == plan.size());
-    if (first) NB_TRY(launch_pass<false>(ctx, plan[k], src, slen, slen, dst, len, n_cols, n, false, src_log));
-    else NB_TRY(launch_pass<false>(ctx, plan[k], dst, len, len, dst, len, n_cols, n, false));
+    if (first) NB_TRY(launch_pass<false>(ctx, plan[k], src, slen, slen, dst, len, n_cols, n, false, src_log, tn));
+    else NB_TRY(launch_pass<false>(ctx, plan[k], dst, len, len, dst, len, n_cols, n, false, 0xffffffffu, tn));
   }
   return NB200_OK;
 }

@@ -290,11 +290,15 @@ static nb200_status launch_interp(nb200_ctx* ctx, InterpArgs& a, u32 domain_log)
 // Evaluate the component's constraints on its evaluation domain and accumulate  sum_k coeff_k * c_k / vanishing  into acc.
 // mask_cols[m]: device pointer of mask m's column evaluated on CanonicCoset(eval_log).circle_domain().
 nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk) {
+                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk, u32 rows_log, u32 dom_log) {
   NB_ARG(ctx, mask_cols.size() == c.masks.size() && coeffs.size() == c.n_constraints, "constraint_eval: shape");
-  const u32 elog = c.eval_log();
-  // vanishing inverses: coset_vanishing(CanonicCoset(log_size).coset, eval_domain.at(i)) for i < 2^log_expand, bit-reversed
-  std::vector<u32> dinv((size_t)1 << c.log_expand);
+  // rows [0, 2^rows_log) of CanonicCoset(dom_log).circle_domain() in bit-reversed order: the whole domain or its first half
+  if (rows_log == 0 && dom_log == 0) rows_log = dom_log = c.eval_log();
+  NB_ARG(ctx, dom_log > c.log_size && (rows_log == dom_log || rows_log + 1 == dom_log) && rows_log >= c.log_size, "constraint_eval: row range");
+  const u32 elog = dom_log;
+  // vanishing inverses: coset_vanishing(CanonicCoset(log_size).coset, eval_domain.at(i)) for i < 2^(dom_log - log_size), bit-reversed
+  // (the vanishing polynomial is constant on each block of 2^log_size rows; a first-half row range uses the first half of the table)
+  std::vector<u32> dinv((size_t)1 << (dom_log - c.log_size));
   {
     HCircleDomain ed = HCircleDomain::canonic(elog);
     HCoset tc = HCoset::odds(c.log_size);
@@ -303,7 +307,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
     for (size_t i = 0; i < dinv.size(); ++i) {
       u32 x = index_to_point(idx_add(ed.index_at(i), shift)).x;
       for (u32 k = 1; k < c.log_size; ++k) x = m31_double_x(x);
-      dinv[bit_reverse_u32((u32)i, c.log_expand)] = m31_inv(x);
+      dinv[bit_reverse_u32((u32)i, dom_log - c.log_size)] = m31_inv(x);
     }
   }
   std::vector<MaskDev> hm(c.masks.size());
@@ -317,7 +321,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_dinv, dinv.size() * 4));
   NB_CUDA(ctx, cudaMemcpyAsync(d_dinv, dinv.data(), dinv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   nb200_status st;
-  if (jk && jk->kernel && jk->eval_log == elog && jk->log_size == c.log_size) {
+  if (jk && jk->kernel && jk->log_size == c.log_size && ((size_t)1 << rows_log) >= JIT_BLOCK) {
     // NVRTC-specialised kernel (jit.cu): same arithmetic, registers instead of the shared-memory register file
     const u32** d_cols = nullptr;
     NB_CUDA(ctx, dmalloc(ctx, (void**)&d_cols, mask_cols.size() * sizeof(u32*)));
@@ -327,7 +331,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
     u32* d_tab = nullptr;
     NB_CUDA(ctx, dmalloc(ctx, (void**)&d_tab, tab.size() * 4 + 16));
     NB_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_tab, d_dinv, acc);
+    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_tab, d_dinv, acc, rows_log, dom_log);
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, (void*)d_cols); dfree(ctx, d_tab);
   } else {
@@ -336,7 +340,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
     a.nb = c.n_base_regs; a.ne = c.n_ext_regs; a.log_size = c.log_size; a.eval_log = elog;
     a.coeff = d_coeff; a.dinv = d_dinv;
     for (int k = 0; k < 4; ++k) a.acc[k] = acc[k];
-    st = launch_interp<false>(ctx, a, elog);
+    st = launch_interp<false>(ctx, a, rows_log);
   }
   // host vectors were consumed by async copies: make sure they are done before the vectors die
   cudaStreamSynchronize(ctx->stream);

@@ -96,9 +96,9 @@ __device__ __forceinline__ Q qmac_tab(Q acc, Q x, const u32* t) {
 std::string gen_source(const AirComponent& c) {
   std::ostringstream o;
   o << kPrelude;
-  const u32 EL = c.eval_log(), DL = c.log_size;
+  const u32 DL = c.log_size;  // EL (the canonic domain the rows belong to) is a kernel argument: whole domains and half domains share the kernel
   // offset_bit_reversed_circle_domain_index with the domain sizes baked in
-  o << "__device__ __forceinline__ u32 offrow(u32 i, int off) { const u32 EL = " << EL << ", DL = " << DL << ";\n"
+  o << "__device__ __forceinline__ u32 offrow(u32 i, int off, u32 EL) { const u32 DL = " << DL << ";\n"
     << "  u32 prev = __brev(i) >> (32 - EL); u32 half = 1u << (EL - 1); long long step = (long long)off * (1ll << (EL - DL - 1)); long long v;\n"
     << "  if (prev < half) { v = ((long long)prev + step) % (long long)half; if (v < 0) v += half; }\n"
     << "  else { v = ((long long)prev - step) % (long long)half; if (v < 0) v += half; v += half; }\n"
@@ -108,7 +108,7 @@ std::string gen_source(const AirComponent& c) {
   auto ld = [&](u32 m) {
     std::ostringstream s;
     if (c.masks[m].off == 0) s << "__ldg(cols[" << m << "] + row)";
-    else s << "__ldg(cols[" << m << "] + offrow(row, " << c.masks[m].off << "))";
+    else s << "__ldg(cols[" << m << "] + offrow(row, " << c.masks[m].off << ", EL))";
     return s.str();
   };
   size_t CH = 250;
@@ -116,7 +116,7 @@ std::string gen_source(const AirComponent& c) {
   size_t n_chunks = (c.prog.size() + CH - 1) / CH;
   u32 k = 0;
   for (size_t ci = 0; ci < n_chunks; ++ci) {
-    o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff, u32 row) {\n";
+    o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff, u32 row, u32 EL) {\n";
     o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q rr = s.rr;\n";
     o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
     for (size_t pc = ci * CH; pc < std::min(c.prog.size(), (ci + 1) * CH); ++pc) {
@@ -151,10 +151,10 @@ std::string gen_source(const AirComponent& c) {
   // of KB of straight-line code at a time, so the instruction cache serves them from one fetch (without the barriers the
   // warps drift apart over the ~0.5 MB program and the kernel is instruction-fetch bound: stall_no_instruction 11 per issue).
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
-    << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3) {\n"
+    << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL) {\n"
     << "  const u32 row = blockIdx.x * " << JIT_BLOCK << " + threadIdx.x;\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
-  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row);\n  __syncthreads();\n";
+  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row, EL);\n  __syncthreads();\n";
   o << "  const u32 di = __ldg(dinv + (row >> " << DL << "));\n"
     << "  a0[row] = add(a0[row], mul(s.rr.c0, di)); a1[row] = add(a1[row], mul(s.rr.c1, di));\n"
     << "  a2[row] = add(a2[row], mul(s.rr.c2, di)); a3[row] = add(a3[row], mul(s.rr.c3, di));\n}\n";
@@ -179,7 +179,6 @@ nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitK
   out->lib = nullptr; out->kernel = nullptr; out->tried = true;
   Nvrtc& n = nvrtc();
   if (!n.ok) return set_err(ctx, NB200_ERR_STATE, "jit: libnvrtc not available");
-  if (((size_t)1 << c.eval_log()) < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");  // grid must be a whole number of blocks
   std::string src = gen_source(c);
   nvrtcProgram prog;
   if (n.CreateProgram(&prog, src.c_str(), "nb200_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return set_err(ctx, NB200_ERR_STATE, "jit: nvrtcCreateProgram failed");
@@ -217,10 +216,13 @@ void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out) {
   }
 }
 
-nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4]) {
-  size_t rows = (size_t)1 << jk.eval_log;
+nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4],
+                                    u32 rows_log, u32 dom_log) {
+  size_t rows = (size_t)1 << rows_log;
+  if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
+  u32 el = dom_log;
   u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
-  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3};
+  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3, (void*)&el};
   cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / JIT_BLOCK)), dim3(JIT_BLOCK), args, 0, ctx->stream);
   ctx->launches += 1;
   if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));

@@ -21,7 +21,7 @@ bool jit_enabled();
 std::string jit_source(const AirComponent& c);  // the CUDA C the component is specialised to (inspection / offline ptxas checks)
 nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out);
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff,
-                                    const u32* d_dinv, u32* const acc[4]);
+                                    const u32* d_dinv, u32* const acc[4], u32 rows_log, u32 dom_log);
 void jit_release(JitKernel& jk);
 void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out);
 

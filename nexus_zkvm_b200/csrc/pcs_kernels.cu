@@ -170,6 +170,34 @@ nb200_status add_inplace(nb200_ctx* ctx, u32* a, const u32* b, size_t n) {
   return NB200_OK;
 }
 
+// a[i] = (a[i] - b[i]) / t, t = the top-layer (line layer tw_log - 1) twiddle of CanonicCoset(tw_log)'s FFT on the first half of the domain.
+// Used to split a polynomial of 2^tw_log coefficients into its low and high halves from evaluations on two half-size domains (prove.cu).
+__global__ void sub_scale_kernel(u32* __restrict__ a, const u32* __restrict__ b, size_t n, const u32* __restrict__ itw_top) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 it = __ldg(itw_top);
+  if (i < n) a[i] = m31_mul(m31_sub(a[i], b[i]), it);
+}
+nb200_status sub_scale_top_twiddle(nb200_ctx* ctx, u32* a, const u32* b, size_t n, u32 tw_log) {
+  NB_ARG(ctx, ctx->tw.d_itw && tw_log >= 2 && ctx->tw.half_log + 1 >= tw_log, "sub_scale_top_twiddle: twiddles");
+  // TwiddleTree layout: the array of layer i of canonic(n) starts at tw_len - 2^(n - i); layer n - 1 has one entry
+  const u32* it = ctx->tw.d_itw + (((size_t)1 << ctx->tw.half_log) - 2);
+  u32 thr = 256;
+  sub_scale_kernel<<<(u32)((n + thr - 1) / thr), thr, 0, ctx->stream>>>(a, b, n, it);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+// dst[c * dst_stride + i] += src[c * src_stride + i], i < len
+__global__ void add_cols_kernel(u32* __restrict__ dst, size_t dst_stride, const u32* __restrict__ src, size_t src_stride, size_t len) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) { u32* d = dst + blockIdx.y * dst_stride + i; *d = m31_add(*d, src[blockIdx.y * src_stride + i]); }
+}
+nb200_status add_cols_strided(nb200_ctx* ctx, u32* dst, size_t dst_stride, const u32* src, size_t src_stride, size_t len, size_t n_cols) {
+  u32 thr = 256;
+  add_cols_kernel<<<dim3((u32)((len + thr - 1) / thr), (u32)n_cols), thr, 0, ctx->stream>>>(dst, dst_stride, src, src_stride, len);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
 // ---- proof of work: smallest nonce with trailing_zeros(Blake2s(digest || nonce_le)) >= pow_bits ----
 __global__ void grind_kernel(const u32 d0, const u32 d1, const u32 d2, const u32 d3, const u32 d4, const u32 d5, const u32 d6, const u32 d7,
                              u64 base, u32 pow_bits, unsigned long long* __restrict__ result) {

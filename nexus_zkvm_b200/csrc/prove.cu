@@ -234,40 +234,62 @@ static nb200_status positions_and_witness(nb200_ctx* ctx, const nb200_cols* col4
 
 static qm31 load_param(const u32* p) { return qm31_make(p[0], p[1], p[2], p[3]); }
 
-// ComponentProver::evaluate_constraint_quotients_on_domain for one component: extend every batch the component reads to
-// its evaluation domain, run the (JIT-specialised or interpreted) constraint kernel, accumulate into `accum` (4 columns).
-nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_idx, const u32* d_params, const std::vector<qm31>& coeff, nb200_cols* accum) {
+// How a component's quotients are evaluated (always the same polynomial, hence the same composition coefficients):
+//   Q_FULL   on CanonicCoset(eval_log).circle_domain(), the reference's domain: every polynomial is extended to it
+//            (or, when eval_log equals the committed LDE size, the committed evaluations are used as they are);
+//   Q_HALF   when eval_log = LDE size + 1: on the committed LDE domain D1 = CanonicCoset(eval_log - 1).circle_domain() (no transform
+//            at all) and on D2 = the first half of CanonicCoset(eval_log).circle_domain() (a half-size transform).  In the circle-FFT
+//            basis a polynomial with coefficients [lo | hi] is lo + pi^(eval_log-2)(x) * hi, and pi^(eval_log-2)(x) vanishes on D1 and is
+//            the constant top-layer twiddle t on D2, so  lo = interpolate_D1(q|D1)  and  hi = interpolate_D2((q|D2 - lo|D2) / t).
+//            Halves the extension work (the largest stage of prove at 2^20 rows).
+enum QuotMode { Q_FULL = 0, Q_HALF = 1 };
+static QuotMode quotient_mode(const nb200_scheme* s, const AirComponent& c) {
+  const u32 lde = c.log_size + s->log_blowup;
+  return (c.eval_log() == lde + 1 && lde > 8) ? Q_HALF : Q_FULL;   // the half-domain transforms need more than 2^8 points (fft.cu)
+}
+
+// ComponentProver::evaluate_constraint_quotients_on_domain for one component: bring every column the component reads onto
+// the evaluation rows, run the (JIT-specialised or interpreted) constraint kernel, ADD into the accumulators.
+//   Q_FULL: accum = 4 columns of 2^eval_log (evaluations on the canonic domain);
+//   Q_HALF: accum = q on D1, accum_hi = q on D2, each 4 columns of 2^(eval_log - 1).
+nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_idx, const u32* d_params, const std::vector<qm31>& coeff,
+                                 QuotMode mode, nb200_cols* accum, nb200_cols* accum_hi) {
   nb200_ctx* ctx = s->ctx;
   const AirProgram& air = air_h->prog;
   NB_ARG(ctx, comp_idx < air.comps.size(), "constraint quotients: component index");
   if (air_h->jit.size() != air.comps.size()) air_h->jit.resize(air.comps.size());
   const AirComponent& c = air.comps[comp_idx];
-  const u32 elog = c.eval_log();
-  NB_ARG(ctx, accum && accum->n_cols == 4 && accum->log_size == elog, "constraint quotients: accumulator must be 4 columns of the evaluation domain size");
+  const u32 elog = c.eval_log(), lde_log = c.log_size + s->log_blowup;
+  if (mode == Q_HALF) NB_ARG(ctx, elog == lde_log + 1 && accum && accum_hi && accum->n_cols == 4 && accum_hi->n_cols == 4 && accum->log_size == lde_log && accum_hi->log_size == lde_log,
+                             "constraint quotients: half-domain accumulators");
+  else NB_ARG(ctx, accum && accum->n_cols == 4 && accum->log_size == elog, "constraint quotients: accumulator must be 4 columns of the evaluation domain size");
   NB_ARG(ctx, coeff.size() == c.n_constraints, "constraint quotients: one coefficient per constraint");
   NB_TRY(twiddles_prepare(ctx, elog));
+  const bool reuse_lde = (mode == Q_FULL && elog == lde_log);
   std::map<std::pair<u32, u32>, nb200_cols*> ext;
   auto free_ext = [&]() { for (auto& kv : ext) nb200_cols_free(ctx, kv.second); ext.clear(); };
-  std::vector<const u32*> mask_cols(c.masks.size());
+  std::vector<const u32*> mask_cols(c.masks.size()), mask_lde(c.masks.size());
   nb200_status st = NB200_OK;
   for (size_t m = 0; m < c.masks.size() && st == NB200_OK; ++m) {
     const AirMask& mk = c.masks[m];
     if (mk.tree >= s->trees.size() || mk.col >= s->trees[mk.tree].cols.size()) { st = set_err(ctx, NB200_ERR_ARG, "prove: AIR references a column that was not committed"); break; }
     const SchemeTree::ColLoc& loc = s->trees[mk.tree].cols[mk.col];
     if (loc.log != c.log_size) { st = set_err(ctx, NB200_ERR_ARG, "prove: column size differs from its component's log_size"); break; }
+    mask_lde[m] = s->trees[mk.tree].ldes[loc.batch]->col(loc.idx);
+    if (reuse_lde) { mask_cols[m] = mask_lde[m]; continue; }
     auto key = std::make_pair(mk.tree, loc.batch);
     if (!ext.count(key)) {
       const nb200_cols* co = s->trees[mk.tree].coeffs[loc.batch];
       nb200_cols* e = nullptr;
-      st = nb200_cols_alloc(ctx, co->n_cols, elog, &e);
+      st = nb200_cols_alloc(ctx, co->n_cols, mode == Q_HALF ? lde_log : elog, &e);
       if (st != NB200_OK) break;
       ext[key] = e;
-      st = fft_evaluate(ctx, co->d, co->log_size, e->d, elog, co->n_cols);
+      if (mode == Q_HALF) st = fft_evaluate(ctx, co->d, co->log_size, e->d, lde_log, co->n_cols, elog);   // first half of canonic(elog)
+      else st = fft_evaluate(ctx, co->d, co->log_size, e->d, elog, co->n_cols);
     }
     if (st == NB200_OK) mask_cols[m] = ext[key]->col(loc.idx);
   }
   if (st == NB200_OK) {
-    u32* accp[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
     JitKernel& jk = air_h->jit[comp_idx];
     trace_mark(ctx, "constraints: extend columns");
     if (!jk.tried) {
@@ -279,10 +301,35 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
         trace_mark(ctx, "jit: compile (one-time)");
       }
     }
-    st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jk.kernel ? &jk : nullptr);
+    const JitKernel* jp = jk.kernel ? &jk : nullptr;
+    if (mode == Q_HALF) {
+      u32* lo[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
+      u32* hi[4] = {accum_hi->col(0), accum_hi->col(1), accum_hi->col(2), accum_hi->col(3)};
+      st = constraint_eval(ctx, c, mask_lde, d_params, coeff, lo, jp, lde_log, lde_log);                        // D1: the committed LDE
+      if (st == NB200_OK) st = constraint_eval(ctx, c, mask_cols, d_params, coeff, hi, jp, lde_log, elog);     // D2: first half of canonic(elog)
+    } else {
+      u32* accp[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
+      st = constraint_eval(ctx, c, mask_cols, d_params, coeff, accp, jp, elog, elog);
+    }
+    trace_mark(ctx, "constraints: row kernel");
   }
   free_ext();
   return st;
+}
+
+// coefficients (4 columns of 2^elog, circle-FFT basis) of the quotient polynomial held by a Q_HALF accumulator pair; lo/hi are consumed
+static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* hi, u32 elog, u32* out /* 4 columns, stride 2^elog */) {
+  const u32 h = elog - 1;
+  const size_t hl = (size_t)1 << h;
+  NB_TRY(fft_interpolate(ctx, lo->d, lo->d, 4, h));                 // lo = coefficients of q mod pi^(elog-2)
+  ColsGuard t(ctx);
+  NB_TRY(nb200_cols_alloc(ctx, 4, h, &t.c));
+  NB_TRY(fft_evaluate(ctx, lo->d, h, t.c->d, h, 4, elog));          // lo evaluated on D2
+  NB_TRY(sub_scale_top_twiddle(ctx, hi->d, t.c->d, 4 * hl, elog));  // (q|D2 - lo|D2) / t
+  NB_TRY(fft_interpolate(ctx, hi->d, hi->d, 4, h, elog));           // hi coefficients
+  NB_TRY(add_cols_strided(ctx, out, (size_t)1 << elog, lo->d, hl, hl, 4));
+  NB_TRY(add_cols_strided(ctx, out + hl, (size_t)1 << elog, hi->d, hl, hl, 4));
+  return NB200_OK;
 }
 
 // QuotientOps::accumulate_quotients on CanonicCoset(log_size).circle_domain(): out (4 columns) = sum over the sample batches
@@ -338,42 +385,53 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(params.size(), 1) * 16));
   if (!params.empty()) NB_CUDA(ctx, cudaMemcpyAsync(d_params, params.data(), params.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
 
-  std::map<u32, nb200_cols*> acc;  // eval_log -> 4-column accumulator
-  auto free_acc = [&]() { for (auto& kv : acc) nb200_cols_free(ctx, kv.second); acc.clear(); };
+  // accumulators per (evaluation log, mode): Q_FULL -> {evals on canonic(elog), -}; Q_HALF -> {q on D1, q on D2}
+  struct Acc { nb200_cols* a = nullptr; nb200_cols* b = nullptr; };
+  std::map<std::pair<u32, int>, Acc> acc;
+  auto free_acc = [&]() { for (auto& kv : acc) { if (kv.second.a) nb200_cols_free(ctx, kv.second.a); if (kv.second.b) nb200_cols_free(ctx, kv.second.b); } acc.clear(); };
+  auto zeroed = [&](u32 lg, nb200_cols** out) -> nb200_status {
+    NB_TRY(nb200_cols_alloc(ctx, 4, lg, out));
+    NB_CUDA(ctx, cudaMemsetAsync((*out)->d, 0, ((size_t)16) << lg, ctx->stream));
+    return NB200_OK;
+  };
   size_t g0 = 0;
   for (const AirComponent& c : air.comps) {
     const u32 elog = c.eval_log();
+    const QuotMode mode = quotient_mode(s, c);
     nb200_status st = NB200_OK;
-    if (!acc.count(elog)) {
-      nb200_cols* a = nullptr;
-      st = nb200_cols_alloc(ctx, 4, elog, &a);
-      if (st == NB200_OK) { acc[elog] = a; if (cudaMemsetAsync(a->d, 0, ((size_t)16) << elog, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "memset"); }
+    auto key = std::make_pair(elog, (int)mode);
+    if (!acc.count(key)) {
+      Acc a;
+      st = zeroed(mode == Q_HALF ? elog - 1 : elog, &a.a);
+      if (st == NB200_OK && mode == Q_HALF) st = zeroed(elog - 1, &a.b);
+      acc[key] = a;
     }
     if (st == NB200_OK) {
       std::vector<qm31> coeff(c.n_constraints);
       for (u32 k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
-      st = component_quotients(s, air_h, &c - &air.comps[0], d_params, coeff, acc[elog]);
+      st = component_quotients(s, air_h, &c - &air.comps[0], d_params, coeff, mode, acc[key].a, acc[key].b);
     }
     g0 += c.n_constraints;
     if (st != NB200_OK) { free_acc(); dfree(ctx, d_params); return st; }
   }
-  trace_mark(ctx, "constraint quotients");
-  // DomainEvaluationAccumulator::finalize: fold the per-size accumulators upwards
-  nb200_cols* cur = nullptr;  // coefficients of the running composition (4 columns)
-  for (auto& kv : acc) {
-    nb200_cols* a = kv.second;
-    if (cur) {
-      ColsGuard tmp(ctx);
-      NB_TRY(nb200_cols_alloc(ctx, 4, kv.first, &tmp.c));
-      NB_TRY(fft_evaluate(ctx, cur->d, cur->log_size, tmp.c->d, kv.first, 4));
-      NB_TRY(add_inplace(ctx, a->d, tmp.c->d, (size_t)4 << kv.first));
-      nb200_cols_free(ctx, cur);
+  // DomainEvaluationAccumulator::finalize.  Upstream folds the per-size accumulators upwards (evaluate the running polynomial on the next
+  // size, add, interpolate); interpolation is linear, so the result is the sum of the zero-extended coefficient vectors — computed here.
+  nb200_cols* cur = nullptr;  // coefficients of the composition (4 columns of 2^comp_log)
+  {
+    nb200_status st = zeroed(comp_log, &cur);
+    for (auto& kv : acc) {
+      if (st != NB200_OK) break;
+      const u32 elog = kv.first.first;
+      if (kv.first.second == Q_HALF) st = half_to_coeffs(ctx, kv.second.a, kv.second.b, elog, cur->d);
+      else {
+        st = fft_interpolate(ctx, kv.second.a->d, kv.second.a->d, 4, elog);
+        if (st == NB200_OK) st = add_cols_strided(ctx, cur->d, (size_t)1 << comp_log, kv.second.a->d, (size_t)1 << elog, (size_t)1 << elog, 4);
+      }
     }
-    NB_TRY(fft_interpolate(ctx, a->d, a->d, 4, kv.first));
-    cur = a; kv.second = nullptr;
+    free_acc();
+    if (st != NB200_OK) { if (cur) nb200_cols_free(ctx, cur); dfree(ctx, d_params); return st; }
   }
-  acc.clear();
-  NB_ARG(ctx, cur != nullptr && cur->log_size == comp_log, "prove: no constraints");
+  NB_ARG(ctx, n_total > 0, "prove: no constraints");
   // tree 3: the composition's 4 coordinate polynomials
   {
     SchemeTree t;
@@ -386,7 +444,7 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     s->trees.push_back(std::move(t));
   }
 
-  trace_mark(ctx, "composition commit");
+  trace_mark(ctx, "composition: coefficients + commit");
   // ---------------- OODS sampling ----------------
   qpoint oods;
   {
@@ -826,7 +884,7 @@ nb200_status nb200_constraint_quotients(nb200_scheme* s, const nb200_air* air, u
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(n_params, 1) * 16));
   nb200_status st = NB200_OK;
   if (n_params && cudaMemcpyAsync(d_params, params, n_params * 16, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "h2d");
-  if (st == NB200_OK) st = component_quotients(s, const_cast<nb200_air*>(air), component, d_params, cf, accum);
+  if (st == NB200_OK) st = component_quotients(s, const_cast<nb200_air*>(air), component, d_params, cf, Q_FULL, accum, nullptr);
   // params is caller memory: make sure the copy has been consumed before returning
   if (st == NB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "sync");
   dfree(ctx, d_params);
