@@ -151,9 +151,14 @@ nb200_status nb200_air_load(nb200_ctx*, const uint32_t* words, size_t n_words, n
 void nb200_air_free(nb200_air*);
 uint32_t nb200_air_n_params(const nb200_air*);
 uint32_t nb200_air_n_components(const nb200_air*);
-/* the CUDA C source a component's constraint program is specialised to at first use (NVRTC, sm_100a); malloc'ed,
- * NUL-terminated, free with nb200_free.  Works without a device (ctx may have been NULL at nb200_air_load). */
-nb200_status nb200_air_kernel_source(const nb200_air*, uint32_t component, char** out);
+/* the CUDA C source a component's programs are specialised to at first use (NVRTC, sm_100a): which = 0 the constraint
+ * program, 1 the logup (interaction trace) program.  malloc'ed, NUL-terminated, free with nb200_free.  Works without a
+ * device (ctx may have been NULL at nb200_air_load).  NB200_ERR_STATE (and *out = NULL): the program is too short to be
+ * specialised and runs on the bytecode interpreter. */
+nb200_status nb200_air_kernel_source(const nb200_air*, uint32_t component, int which, char** out);
+/* file name (16 hex digits + ".cubin") under which that kernel is looked up in the cubin cache: <library dir>/jit_cache or
+ * $NB200_JIT_CACHE.  `python -m nexus_zkvm_b200.build` pre-compiles the shipped machines' kernels there with nvcc. */
+uint64_t nb200_kernel_source_key(const char* source);
 
 /* ---- CommitmentSchemeProver<B, Blake2sMerkleChannel> (machine.rs:202-203) ------------------------------ */
 typedef struct nb200_scheme nb200_scheme;

@@ -70,5 +70,76 @@ def build(force=False, verbose=False):
     return LIB
 
 
+# ---- cubin cache for the run-time specialised AIR kernels (csrc/jit.cu) ---------------------------------------------
+JIT_CACHE = os.path.join(HERE, "jit_cache")
+# (log_size, n_lanes, logup_in_pairs): bench.py / tools/prove_trace.py, __graft_entry__.smoke and the machines of tests/test_gpu_*.py
+SHIPPED_MACHINES = [(20, 21, False), (8, 1, False), (8, 2, False), (8, 2, True), (8, 3, False), (9, 1, False), (9, 2, False),
+                    (9, 2, True), (10, 1, False), (12, 3, False)]
+
+
+def kernel_sources(words):
+    """[(cache key, CUDA C source)] of the kernels the library specialises for an AIR (no GPU needed)."""
+    import ctypes as C
+    import numpy as np
+    L = C.CDLL(LIB)
+    L.nb200_kernel_source_key.restype = C.c_uint64
+    L.nb200_kernel_source_key.argtypes = [C.c_char_p]
+    L.nb200_air_n_components.restype = C.c_uint32
+    L.nb200_air_n_components.argtypes = [C.c_void_p]
+    L.nb200_free.argtypes = [C.c_void_p]
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    air = C.c_void_p()
+    if L.nb200_air_load(None, w.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(w.size), C.byref(air)) != 0:
+        raise RuntimeError("nb200_air_load failed")
+    out = []
+    for comp in range(L.nb200_air_n_components(air)):
+        for which in (0, 1):
+            p = C.c_void_p()
+            if L.nb200_air_kernel_source(air, C.c_uint32(comp), C.c_int(which), C.byref(p)) != 0 or not p:
+                continue
+            src = C.string_at(p)
+            L.nb200_free(p)
+            out.append((int(L.nb200_kernel_source_key(src)), src))
+    L.nb200_air_free(air)
+    return out
+
+
+def precompile_kernels(machines=SHIPPED_MACHINES, verbose=False):
+    """Compile the AIR kernels of the shipped machines with nvcc into jit_cache/<key>.cubin (what NVRTC would produce on
+    first use): a fresh GPU box then neither pages in libnvrtc nor compiles."""
+    from . import machine as M
+    os.makedirs(JIT_CACHE, exist_ok=True)
+    todo = {}
+    for log_size, lanes, pairs in machines:
+        m = M.AddMachine(log_size=log_size, n_lanes=lanes, logup_in_pairs=pairs)
+        for key, src in kernel_sources(m.words):
+            path = os.path.join(JIT_CACHE, f"{key:016x}.cubin")
+            if not os.path.exists(path):
+                todo[path] = src
+
+    def run(item):
+        path, src = item
+        cu = path[:-6] + ".cu"
+        with open(cu, "wb") as f:
+            f.write(src)
+        cmd = [NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-cubin", cu, "-o", path + ".tmp"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        os.remove(cu)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on a generated kernel:\n" + r.stderr[-2000:])
+        os.replace(path + ".tmp", path)
+        return path
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
+            for path in ex.map(run, sorted(todo.items())):
+                if verbose:
+                    sys.stderr.write("cubin " + path + "\n")
+    return len(todo)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--no-kernels" not in sys.argv:
+        n = precompile_kernels(verbose="--verbose" in sys.argv)
+        print(f"jit_cache: {n} kernel(s) compiled")

@@ -465,6 +465,7 @@ static void plan_passes(u32 n, std::vector<PassPlan>& out) {
   u32 LA = n - npass * 8;                     // give the strided passes 8 layers each when possible
   if (LA < 9) LA = 9;
   if (LA > 13) LA = 13;
+  if (const char* e = getenv("NB200_FFT_LA")) { u32 v = (u32)atoi(e); if (v >= 9 && v <= 13 && n - v <= 9 * npass && n > v) LA = v; }  // tuning knob
   out.push_back(PassPlan{0, LA, 0});
   u32 rest = n - LA, lo = LA;
   for (u32 k = 0; k < npass; ++k) {

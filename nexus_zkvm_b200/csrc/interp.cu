@@ -351,7 +351,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
 // LogupTraceGenerator: fills 4 * n_logup_cols columns (bit-reversed circle-domain order) and returns the claimed sum.
 // mask_cols[m]: device pointer of mask m's trace column on the trace domain (nullptr for masks the program never reads).
 nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                            u32* d_out, qm31* claimed) {
+                            u32* d_out, qm31* claimed, const JitKernel* jk) {
   const u32 ncols = c.n_logup_cols();
   *claimed = qm31_zero();
   if (ncols == 0) return NB200_OK;
@@ -368,7 +368,20 @@ nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::ve
   a.prog = d_prog; a.n_instr = (u32)c.logup_prog.size(); a.masks = d_masks; a.params = d_params;
   a.nb = c.lg_base_regs; a.ne = c.lg_ext_regs; a.log_size = c.log_size; a.eval_log = c.log_size;
   a.batching = d_batch; a.out = d_out; a.n_batches = ncols;
-  NB_TRY(launch_interp<true>(ctx, a, c.log_size));
+  if (jk && jk->kernel && jk->log_size == c.log_size && ((size_t)1 << c.log_size) >= JIT_BLOCK) {
+    // NVRTC-specialised kernel (jit.cu gen_logup_source): same arithmetic as the bytecode loop below
+    std::vector<const u32*> ptrs(hm.size());
+    for (size_t m = 0; m < hm.size(); ++m) ptrs[m] = hm[m].ptr;
+    const u32** d_cols = nullptr;
+    NB_CUDA(ctx, dmalloc(ctx, (void**)&d_cols, std::max<size_t>(ptrs.size(), 1) * sizeof(u32*)));
+    NB_CUDA(ctx, cudaMemcpyAsync(d_cols, ptrs.data(), ptrs.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
+    nb200_status js = jit_launch_logup(ctx, *jk, d_cols, d_params, d_out, c.log_size);
+    cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, (void*)d_cols);
+    NB_TRY(js);
+  } else {
+    NB_TRY(launch_interp<true>(ctx, a, c.log_size));
+  }
   // finalize_last: claimed sum of the last secure column, shift by claimed/2^n, prefix sum in coset order
   const size_t n = (size_t)1 << c.log_size;
   u32* last = d_out + ((size_t)(4 * (ncols - 1)) << c.log_size);

@@ -11,6 +11,9 @@
 #include "pcs.h"
 #include "jit.h"
 #include <dlfcn.h>
+#include <unistd.h>
+#include <cstring>
+#include <cstdio>
 #include <nvrtc.h>
 #include <sstream>
 #include <cstdlib>
@@ -85,6 +88,23 @@ __device__ __forceinline__ Q qmul(Q x, Q y) {
   u32 gp = add(add(y.c3, y.c3), y.c2), g = sub(add(y.c2, y.c2), y.c3);
   return qmac(Q{0u, 0u, 0u, 0u}, x, y.c0, y.c1, y.c2, y.c3, P31 - y.c1, P31 - y.c3, g, gp, P31 - gp);
 }
+// x^(P-2): 30 squarings + 8 products
+__device__ __forceinline__ u32 sqn(u32 x, int n) { for (int i = 0; i < n; ++i) x = mul(x, x); return x; }
+__device__ __forceinline__ u32 minv(u32 x) {
+  u32 a2 = mul(sqn(x, 1), x), a4 = mul(sqn(a2, 2), a2), a8 = mul(sqn(a4, 4), a4), a16 = mul(sqn(a8, 8), a8);
+  u32 a24 = mul(sqn(a16, 8), a8), a28 = mul(sqn(a24, 4), a4), a29 = mul(sqn(a28, 1), x);
+  return mul(sqn(a29, 2), x);
+}
+// (a + bu)^-1 = (a - bu) / (a^2 - (2 + i) b^2), a, b in CM31 (the formula of m31.cuh qm31_inv); the CM31 inverse is conj / norm
+__device__ __noinline__ Q qinv(Q q) {
+  u32 b2r = sub(mul(q.c2, q.c2), mul(q.c3, q.c3)), b2i = mul(add(q.c2, q.c2), q.c3);           // b^2
+  u32 a2r = sub(mul(q.c0, q.c0), mul(q.c1, q.c1)), a2i = mul(add(q.c0, q.c0), q.c1);           // a^2
+  u32 dr = sub(a2r, sub(add(b2r, b2r), b2i)), di = sub(a2i, add(add(b2i, b2i), b2r));          // a^2 - (2 b^2 + i b^2)
+  u32 ni = minv(add(mul(dr, dr), mul(di, di)));
+  u32 ir = mul(dr, ni), ii = neg(mul(di, ni));                                                 // 1 / denom
+  return Q{sub(mul(q.c0, ir), mul(q.c1, ii)), add(mul(q.c0, ii), mul(q.c1, ir)),
+           neg(sub(mul(q.c2, ir), mul(q.c3, ii))), neg(add(mul(q.c2, ii), mul(q.c3, ir)))};
+}
 __device__ __forceinline__ Q ldq(const u32* p) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); return Q{v.x, v.y, v.z, v.w}; }
 // rr + coeff * x with the coefficient's derived multipliers precomputed by the host (12 words per constraint, see jit_coeff_table)
 __device__ __forceinline__ Q qmac_tab(Q acc, Q x, const u32* t) {
@@ -92,6 +112,30 @@ __device__ __forceinline__ Q qmac_tab(Q acc, Q x, const u32* t) {
   return qmac(acc, x, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x);
 }
 )SRC";
+
+// the arithmetic / load opcodes shared by the constraint and the logup programs
+template <class Ld>
+void emit_op(std::ostringstream& o, const AirInstr& in, Ld ld) {
+  switch (in.op) {
+    case OP_LOADM: o << "b[" << in.dst << "] = " << ld(in.a) << ";"; break;
+    case OP_CONSTB: o << "b[" << in.dst << "] = " << in.a << "u;"; break;
+    case OP_ADDB: o << "b[" << in.dst << "] = add(b[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_SUBB: o << "b[" << in.dst << "] = sub(b[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_MULB: o << "b[" << in.dst << "] = mul(b[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_NEGB: o << "b[" << in.dst << "] = neg(b[" << in.a << "]);"; break;
+    case OP_PARAME: o << "e[" << in.dst << "] = ldq(params + " << 4 * in.a << ");"; break;
+    case OP_ADDE: o << "e[" << in.dst << "] = qadd(e[" << in.a << "], e[" << in.b << "]);"; break;
+    case OP_SUBE: o << "e[" << in.dst << "] = qsub(e[" << in.a << "], e[" << in.b << "]);"; break;
+    case OP_MULE: o << "e[" << in.dst << "] = qmul(e[" << in.a << "], e[" << in.b << "]);"; break;
+    case OP_NEGE: o << "e[" << in.dst << "] = qneg(e[" << in.a << "]);"; break;
+    case OP_ADDEB: o << "e[" << in.dst << "] = qaddb(e[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_SUBEB: o << "e[" << in.dst << "] = qsubb(e[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_MULEB: o << "e[" << in.dst << "] = qmulb(e[" << in.a << "], b[" << in.b << "]);"; break;
+    case OP_BTOE: o << "e[" << in.dst << "] = Q{b[" << in.a << "], 0u, 0u, 0u};"; break;
+    case OP_LOADME: o << "e[" << in.dst << "] = Q{" << ld(in.a) << ", " << ld(in.a + 1) << ", " << ld(in.a + 2) << ", " << ld(in.a + 3) << "};"; break;
+    default: break;
+  }
+}
 
 std::string gen_source(const AirComponent& c) {
   std::ostringstream o;
@@ -123,25 +167,9 @@ std::string gen_source(const AirComponent& c) {
       const AirInstr& in = c.prog[pc];
       o << "  ";
       switch (in.op) {
-        case OP_LOADM: o << "b[" << in.dst << "] = " << ld(in.a) << ";"; break;
-        case OP_CONSTB: o << "b[" << in.dst << "] = " << in.a << "u;"; break;
-        case OP_ADDB: o << "b[" << in.dst << "] = add(b[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_SUBB: o << "b[" << in.dst << "] = sub(b[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_MULB: o << "b[" << in.dst << "] = mul(b[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_NEGB: o << "b[" << in.dst << "] = neg(b[" << in.a << "]);"; break;
-        case OP_PARAME: o << "e[" << in.dst << "] = ldq(params + " << 4 * in.a << ");"; break;
-        case OP_ADDE: o << "e[" << in.dst << "] = qadd(e[" << in.a << "], e[" << in.b << "]);"; break;
-        case OP_SUBE: o << "e[" << in.dst << "] = qsub(e[" << in.a << "], e[" << in.b << "]);"; break;
-        case OP_MULE: o << "e[" << in.dst << "] = qmul(e[" << in.a << "], e[" << in.b << "]);"; break;
-        case OP_NEGE: o << "e[" << in.dst << "] = qneg(e[" << in.a << "]);"; break;
-        case OP_ADDEB: o << "e[" << in.dst << "] = qaddb(e[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_SUBEB: o << "e[" << in.dst << "] = qsubb(e[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_MULEB: o << "e[" << in.dst << "] = qmulb(e[" << in.a << "], b[" << in.b << "]);"; break;
-        case OP_BTOE: o << "e[" << in.dst << "] = Q{b[" << in.a << "], 0u, 0u, 0u};"; break;
-        case OP_LOADME: o << "e[" << in.dst << "] = Q{" << ld(in.a) << ", " << ld(in.a + 1) << ", " << ld(in.a + 2) << ", " << ld(in.a + 3) << "};"; break;
         case OP_CONSTRB: o << "rr = qadd(rr, qmulb(ldq(coeff + " << JIT_COEFF_WORDS * k << "), b[" << in.a << "]));"; ++k; break;
         case OP_CONSTRE: o << "rr = qmac_tab(rr, e[" << in.a << "], coeff + " << JIT_COEFF_WORDS * k << ");"; ++k; break;
-        default: break;
+        default: emit_op(o, in, ld); break;
       }
       o << "\n";
     }
@@ -160,14 +188,64 @@ std::string gen_source(const AirComponent& c) {
     << "  a2[row] = add(a2[row], mul(s.rr.c2, di)); a3[row] = add(a3[row], mul(s.rr.c3, di));\n}\n";
   return o.str();
 }
+
+// LogupTraceGenerator for one component (interp.cu interp_kernel<.., LOGUP> is the bytecode version): run the logup program, combine the
+// fractions of each batch (write_frac), add to the running row sum and store the 4 coordinate columns of the batch (finalize_col).
+// The prefix sum over rows of the last column stays in logup_generate.
+std::string gen_logup_source(const AirComponent& c) {
+  std::ostringstream o;
+  o << kPrelude;
+  const u32 nb = c.lg_base_regs ? c.lg_base_regs : 1, ne = c.lg_ext_regs ? c.lg_ext_regs : 1;
+  o << "struct St { u32 b[" << nb << "]; Q e[" << ne << "]; Q fn, fd, run; };\n";
+  auto ld = [&](u32 m) {
+    std::ostringstream s;
+    // next-row masks and interaction-trace masks are not inputs of the logup program (they read as zero, as in the interpreter)
+    if (m < c.masks.size() && c.masks[m].off == 0 && c.masks[m].tree != 2) s << "__ldg(cols[" << m << "] + row)";
+    else s << "0u";
+    return s.str();
+  };
+  size_t CH = 150;
+  size_t n_chunks = (c.logup_prog.size() + CH - 1) / CH;
+  u32 k = 0; bool have = false; u32 cur_batch = 0;
+  auto finalize = [&](std::ostringstream& o2) {
+    o2 << "  run = qadd(run, qmul(fn, qinv(fd)));\n";
+    for (int cc = 0; cc < 4; ++cc) o2 << "  out[(" << (4 * (size_t)cur_batch + cc) << "ull << LS) + row] = run.c" << cc << ";\n";
+  };
+  for (size_t ci = 0; ci < n_chunks; ++ci) {
+    o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 row, u32 LS) {\n";
+    o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q fn = s.fn, fd = s.fd, run = s.run;\n";
+    o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
+    for (size_t pc = ci * CH; pc < std::min(c.logup_prog.size(), (ci + 1) * CH); ++pc) {
+      const AirInstr& in = c.logup_prog[pc];
+      if (in.op == OP_FRAC) {
+        u32 bt = c.batching[k];
+        if (have && bt != cur_batch) { finalize(o); have = false; }
+        if (!have) o << "  fn = e[" << in.a << "]; fd = e[" << in.b << "];\n";                      // first fraction of the batch: 0/1 + n/d
+        else o << "  fn = qadd(qmul(fn, e[" << in.b << "]), qmul(e[" << in.a << "], fd)); fd = qmul(fd, e[" << in.b << "]);\n";
+        cur_batch = bt; have = true; ++k;
+      } else {
+        o << "  "; emit_op(o, in, ld); o << "\n";
+      }
+    }
+    if (ci + 1 == n_chunks && have) finalize(o);
+    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.fn = fn; s.fd = fd; s.run = run;\n}\n";
+  }
+  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 LS) {\n"
+    << "  const u32 row = blockIdx.x * " << JIT_BLOCK << " + threadIdx.x;\n  St s;\n"
+    << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n"
+    << "  s.fn = Q{0u, 0u, 0u, 0u}; s.fd = Q{1u, 0u, 0u, 0u}; s.run = Q{0u, 0u, 0u, 0u};\n";
+  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, out, row, LS);\n  __syncthreads();\n";
+  o << "}\n";
+  return o.str();
+}
 }  // namespace
 
 std::string jit_source(const AirComponent& c) { return gen_source(c); }
+std::string jit_logup_source(const AirComponent& c) { return gen_logup_source(c); }
 
 bool jit_enabled() {
   const char* e = getenv("NB200_JIT");
-  if (e && e[0] == '0') return false;
-  return nvrtc().ok;
+  return !(e && e[0] == '0');   // libnvrtc itself is only opened when a kernel is missing from the cubin cache
 }
 
 void jit_release(JitKernel& jk) {
@@ -175,11 +253,74 @@ void jit_release(JitKernel& jk) {
   jk = JitKernel();
 }
 
-nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out) {
+static nb200_status jit_compile_source(nb200_ctx* ctx, const AirComponent& c, const std::string& src, JitKernel* out);
+nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out) { return jit_compile_source(ctx, c, gen_source(c), out); }
+nb200_status jit_compile_logup(nb200_ctx* ctx, const AirComponent& c, JitKernel* out) { return jit_compile_source(ctx, c, gen_logup_source(c), out); }
+// ---- cubin cache: <directory of this library>/jit_cache/<key>.cubin (or $NB200_JIT_CACHE).  `python -m nexus_zkvm_b200.build`
+// fills it for the shipped machines with nvcc, so a fresh box neither loads libnvrtc nor compiles; kernels compiled at run time are
+// added when the directory is writable.  The key covers the generated source and the target.
+uint64_t jit_source_key(const std::string& src) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } };
+  mix(src.data(), src.size());
+  const char* tgt = "|sm_100a|nb200-jit-1";
+  mix(tgt, strlen(tgt));
+  return h;
+}
+static std::string jit_cache_dir() {
+  if (const char* e = getenv("NB200_JIT_CACHE")) return e;
+  Dl_info info;
+  if (dladdr((const void*)&jit_source_key, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t k = p.rfind('/');
+    return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/jit_cache";
+  }
+  return "";
+}
+static std::string jit_cache_path(const std::string& src) {
+  std::string d = jit_cache_dir();
+  if (d.empty()) return "";
+  char name[32]; snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)jit_source_key(src));
+  return d + name;
+}
+static bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) { out.resize((size_t)n); ok = fread(out.data(), 1, (size_t)n, f) == (size_t)n; }
+  fclose(f);
+  return ok;
+}
+static void write_file_atomic(const std::string& path, const std::vector<char>& data) {
+  std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+static nb200_status jit_load_cubin(nb200_ctx* ctx, const AirComponent& c, const std::vector<char>& cubin, JitKernel* out) {
+  cudaLibrary_t lib;
+  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryLoadData: ") + cudaGetErrorString(e));
+  cudaKernel_t k;
+  e = cudaLibraryGetKernel(&k, lib, "nbjit");
+  if (e != cudaSuccess) { cudaLibraryUnload(lib); return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryGetKernel: ") + cudaGetErrorString(e)); }
+  out->lib = (void*)lib; out->kernel = (void*)k; out->log_size = c.log_size; out->eval_log = c.eval_log();
+  return NB200_OK;
+}
+
+static nb200_status jit_compile_source(nb200_ctx* ctx, const AirComponent& c, const std::string& src, JitKernel* out) {
   out->lib = nullptr; out->kernel = nullptr; out->tried = true;
+  const std::string cache = jit_cache_path(src);
+  if (!cache.empty()) {
+    std::vector<char> cubin;
+    if (read_file(cache, cubin) && jit_load_cubin(ctx, c, cubin, out) == NB200_OK) return NB200_OK;
+    cudaGetLastError();  // a stale or foreign file: fall through to the compiler
+  }
   Nvrtc& n = nvrtc();
   if (!n.ok) return set_err(ctx, NB200_ERR_STATE, "jit: libnvrtc not available");
-  std::string src = gen_source(c);
   nvrtcProgram prog;
   if (n.CreateProgram(&prog, src.c_str(), "nb200_air.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return set_err(ctx, NB200_ERR_STATE, "jit: nvrtcCreateProgram failed");
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
@@ -194,14 +335,8 @@ nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitK
   std::vector<char> cubin(cs);
   n.GetCUBIN(prog, cubin.data());
   n.DestroyProgram(&prog);
-  cudaLibrary_t lib;
-  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryLoadData: ") + cudaGetErrorString(e));
-  cudaKernel_t k;
-  e = cudaLibraryGetKernel(&k, lib, "nbjit");
-  if (e != cudaSuccess) { cudaLibraryUnload(lib); return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryGetKernel: ") + cudaGetErrorString(e)); }
-  out->lib = (void*)lib; out->kernel = (void*)k; out->log_size = c.log_size; out->eval_log = c.eval_log();
-  return NB200_OK;
+  if (!cache.empty()) write_file_atomic(cache, cubin);
+  return jit_load_cubin(ctx, c, cubin, out);
 }
 
 // per constraint: y0 y1 y2 y3 | P-y1 P-y3 2y2-y3 y2+2y3 | P-(y2+2y3) 0 0 0   (the multipliers of qmac in the generated code)
@@ -214,6 +349,16 @@ void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out) {
     t[0] = y[0]; t[1] = y[1]; t[2] = y[2]; t[3] = y[3];
     t[4] = P31 - y[1]; t[5] = P31 - y[3]; t[6] = g; t[7] = gp; t[8] = P31 - gp;
   }
+}
+
+nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, u32* d_out, u32 log_size) {
+  size_t rows = (size_t)1 << log_size;
+  if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
+  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_out, (void*)&log_size};
+  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / JIT_BLOCK)), dim3(JIT_BLOCK), args, 0, ctx->stream);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));
+  return NB200_OK;
 }
 
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4],

@@ -8,6 +8,7 @@
 namespace nb {
 
 static const u32 JIT_BLOCK = 1024;       // threads per CTA of the generated kernel (one CTA per SM)
+static const u32 JIT_MIN_INSTR = 64;      // shorter programs stay on the bytecode interpreter
 static const u32 JIT_COEFF_WORDS = 12;   // words per constraint in the coefficient table the generated kernel reads
 
 struct JitKernel {
@@ -18,8 +19,12 @@ struct JitKernel {
 };
 
 bool jit_enabled();
+uint64_t jit_source_key(const std::string& src);   // name of the kernel's file in the cubin cache
 std::string jit_source(const AirComponent& c);  // the CUDA C the component is specialised to (inspection / offline ptxas checks)
 nb200_status jit_compile_constraints(nb200_ctx* ctx, const AirComponent& c, JitKernel* out);
+nb200_status jit_compile_logup(nb200_ctx* ctx, const AirComponent& c, JitKernel* out);
+nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, u32* d_out, u32 log_size);
+std::string jit_logup_source(const AirComponent& c);
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff,
                                     const u32* d_dinv, u32* const acc[4], u32 rows_log, u32 dom_log);
 void jit_release(JitKernel& jk);

@@ -31,7 +31,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
 nb200_status sub_scale_top_twiddle(nb200_ctx* ctx, u32* a, const u32* b, size_t n, u32 tw_log);  // a = (a - b) / (top-layer twiddle of canonic(tw_log))
 nb200_status add_cols_strided(nb200_ctx* ctx, u32* dst, size_t dst_stride, const u32* src, size_t src_stride, size_t len, size_t n_cols);
 nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                            u32* d_out, qm31* claimed);
+                            u32* d_out, qm31* claimed, const JitKernel* jk = nullptr);
 
 nb200_status eval_at_points(nb200_ctx* ctx, const u32* coeffs, size_t n_cols, u32 log_size, const u32* points_xy, size_t n_points, u32* out_qm31);
 nb200_status merkle_decommit(nb200_ctx* ctx, const nb200_tree* tree, const std::vector<ColRef>& cols_in,

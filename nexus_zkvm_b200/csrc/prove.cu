@@ -17,8 +17,10 @@
 struct nb200_channel { nb::HostChannel ch; };
 struct nb200_air {
   nb::AirProgram prog;
-  std::vector<nb::JitKernel> jit;  // per component, compiled on first use (NVRTC); empty kernel = interpreter
-  ~nb200_air() { for (auto& j : jit) nb::jit_release(j); }
+  // per component, compiled on first use (NVRTC); empty kernel = bytecode interpreter
+  std::vector<nb::JitKernel> jit;        // constraint program
+  std::vector<nb::JitKernel> jit_logup;  // logup (interaction trace) program
+  ~nb200_air() { for (auto& j : jit) nb::jit_release(j); for (auto& j : jit_logup) nb::jit_release(j); }
 };
 
 namespace nb {
@@ -294,7 +296,7 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
     trace_mark(ctx, "constraints: extend columns");
     if (!jk.tried) {
       jk.tried = true;
-      if (c.prog.size() >= 64 && jit_enabled()) {
+      if (c.prog.size() >= JIT_MIN_INSTR && jit_enabled()) {
         trace_mark(ctx, "jit: load nvrtc (one-time)");
         nb200_status js = jit_compile_constraints(ctx, c, &jk);
         if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for component: %s\n", ctx->err.c_str());
@@ -692,9 +694,11 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
 
 // LogupTraceGenerator over the committed trace (the trace evaluations are passed in by the caller, as in the reference
 // where generate_interaction_trace reads the finalized traces — machine.rs:242-247)
-nb200_status gen_interaction(nb200_ctx* ctx, const AirProgram& air, u32 comp_idx, const nb200_cols* const* tree0, size_t n0, const nb200_cols* const* tree1, size_t n1,
+nb200_status gen_interaction(nb200_ctx* ctx, nb200_air* air_h, u32 comp_idx, const nb200_cols* const* tree0, size_t n0, const nb200_cols* const* tree1, size_t n1,
                              const std::vector<qm31>& params, nb200_cols** out, qm31* claimed) {
+  const AirProgram& air = air_h->prog;
   NB_ARG(ctx, comp_idx < air.comps.size(), "gen_interaction: component index");
+  if (air_h->jit_logup.size() != air.comps.size()) air_h->jit_logup.resize(air.comps.size());
   const AirComponent& c = air.comps[comp_idx];
   std::vector<std::vector<const u32*>> flat(2);
   std::vector<std::vector<u32>> flog(2);
@@ -714,7 +718,16 @@ nb200_status gen_interaction(nb200_ctx* ctx, const AirProgram& air, u32 comp_idx
   nb200_cols* o = nullptr;
   NB_TRY(nb200_cols_alloc(ctx, (size_t)4 * c.n_logup_cols(), c.log_size, &o));
   trace_mark(ctx, nullptr);
-  nb200_status st = logup_generate(ctx, c, mask_cols, d_params, o->d, claimed);
+  JitKernel& jk = air_h->jit_logup[comp_idx];
+  if (!jk.tried) {
+    jk.tried = true;
+    if (c.logup_prog.size() >= JIT_MIN_INSTR && c.n_logup_cols() > 0 && jit_enabled()) {
+      nb200_status js = jit_compile_logup(ctx, c, &jk);
+      if (js != NB200_OK && ctx->trace) fprintf(stderr, "[nb200] jit unavailable for logup program: %s\n", ctx->err.c_str());
+      trace_mark(ctx, "jit: compile logup (one-time)");
+    }
+  }
+  nb200_status st = logup_generate(ctx, c, mask_cols, d_params, o->d, claimed, jk.kernel ? &jk : nullptr);
   trace_mark(ctx, "logup interaction trace");
   cudaStreamSynchronize(ctx->stream);
   dfree(ctx, d_params);
@@ -757,9 +770,13 @@ nb200_status nb200_air_load(nb200_ctx* ctx, const uint32_t* words, size_t n_word
 void nb200_air_free(nb200_air* a) { delete a; }
 uint32_t nb200_air_n_params(const nb200_air* a) { return a ? a->prog.n_params : 0; }
 uint32_t nb200_air_n_components(const nb200_air* a) { return a ? (uint32_t)a->prog.comps.size() : 0; }
-nb200_status nb200_air_kernel_source(const nb200_air* a, uint32_t component, char** out) {
-  if (!a || !out || component >= a->prog.comps.size()) return NB200_ERR_ARG;
-  std::string src = jit_source(a->prog.comps[component]);
+uint64_t nb200_kernel_source_key(const char* src) { return src ? jit_source_key(src) : 0; }
+nb200_status nb200_air_kernel_source(const nb200_air* a, uint32_t component, int which, char** out) {
+  if (!a || !out || component >= a->prog.comps.size() || which < 0 || which > 1) return NB200_ERR_ARG;
+  const AirComponent& c = a->prog.comps[component];
+  *out = nullptr;
+  if ((which == 0 ? c.prog.size() : c.logup_prog.size()) < JIT_MIN_INSTR || (which == 1 && c.n_logup_cols() == 0)) return NB200_ERR_STATE;  // runs on the interpreter
+  std::string src = (which == 0) ? jit_source(c) : jit_logup_source(c);
   char* o = (char*)malloc(src.size() + 1);
   if (!o) return NB200_ERR_OOM;
   memcpy(o, src.c_str(), src.size() + 1);
@@ -797,7 +814,7 @@ nb200_status nb200_gen_interaction_trace(nb200_ctx* ctx, const nb200_air* air, u
   std::vector<qm31> p(n_params);
   if (n_params) memcpy(p.data(), params, n_params * 16);
   qm31 cs;
-  NB_TRY(gen_interaction(ctx, air->prog, component, tree0, n0, tree1, n1, p, out, &cs));
+  NB_TRY(gen_interaction(ctx, const_cast<nb200_air*>(air), component, tree0, n0, tree1, n1, p, out, &cs));
   memcpy(claimed_sum, cs.c, 16);
   return NB200_OK;
 }

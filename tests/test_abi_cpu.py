@@ -51,3 +51,15 @@ def test_product_sources_do_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_kernel_sources_and_cache_keys_without_a_gpu():
+    """The generated CUDA C of an AIR's kernels is available without a device; the cache key is stable and distinguishes kernels."""
+    from nexus_zkvm_b200 import build as B, machine as M
+    a = B.kernel_sources(M.AddMachine(log_size=8, n_lanes=1).words)
+    b = B.kernel_sources(M.AddMachine(log_size=8, n_lanes=2).words)
+    assert len(a) >= 2 and len(b) >= 2               # constraint + logup program of the main component
+    assert all(b"extern \"C\" __global__" in src and b"nbjit" in src for _k, src in a)
+    keys = [k for k, _ in a + b]
+    assert len(set(keys)) == len(keys)
+    assert [k for k, _ in B.kernel_sources(M.AddMachine(log_size=8, n_lanes=1).words)] == [k for k, _ in a]

@@ -122,3 +122,20 @@ def test_interpreter_and_jit_kernels_agree(backend, monkeypatch):
     monkeypatch.setenv("NB200_JIT", "1")
     j_proof, _, _ = M.prove(m, backend, cols, mult)
     assert i_proof == o_proof and j_proof == o_proof
+
+
+def test_nvrtc_path_with_an_empty_cubin_cache(monkeypatch, tmp_path):
+    """The shipped jit_cache/ holds nvcc-built cubins for the machines used here; point the cache at an empty directory so
+    that this proof compiles its kernels with NVRTC at run time, fills the cache, and a second context loads them back."""
+    monkeypatch.setenv("NB200_JIT_CACHE", str(tmp_path))
+    m = M.AddMachine(log_size=8, n_lanes=1)
+    cols, mult = m.fill_main_trace(seed=5)
+    o_proof, _, _ = M.prove(m, OracleBackend(), cols, mult)
+    for _ in range(2):  # first: NVRTC compile + store; second (new AIR handle): load from the cache
+        ctx = nb.Context(0)
+        try:
+            g_proof, _, _ = M.prove(m, CudaBackend(ctx), cols, mult)
+        finally:
+            ctx.close()
+        assert g_proof == o_proof
+    assert len(list(tmp_path.glob("*.cubin"))) >= 1
