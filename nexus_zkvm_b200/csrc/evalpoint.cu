@@ -19,7 +19,7 @@ __device__ __forceinline__ qm31 load_q(const u32* p) { return qm31_make(p[0], p[
 
 __global__ void __launch_bounds__(EP_THREADS) eval_points_partial_kernel(const u32* __restrict__ coeffs, u32 log_size, const u32* __restrict__ factors /* n_points x log_size x 4 */,
                                                                         u32 Q, u32* __restrict__ partials /* [col][point][block][4] */, u32 n_points) {
-  __shared__ u32 wmid[128 * 4];
+  __shared__ __align__(16) u32 wmid[128 * 4];
   __shared__ u32 red[EP_THREADS / 32][4];
   const u32 col = blockIdx.y, pt = blockIdx.z, blk = blockIdx.x;
   const u32 nblk = gridDim.x;
@@ -39,13 +39,13 @@ __global__ void __launch_bounds__(EP_THREADS) eval_points_partial_kernel(const u
     const u32* c = coeffs + ((size_t)col << log_size) + ((size_t)blk << Q);
     u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (u32 j = 0; j < nj; ++j) {
-      u64 v = __ldg(c + ((size_t)j << LB) + t);
-      u64 p0 = v * wmid[4 * j], p1 = v * wmid[4 * j + 1], p2 = v * wmid[4 * j + 2], p3 = v * wmid[4 * j + 3];
-      // fold each product to < 2^32 and accumulate (nj <= 128 terms: no overflow)
-      a0 += (p0 & P31) + (p0 >> 31); a1 += (p1 & P31) + (p1 >> 31);
-      a2 += (p2 & P31) + (p2 >> 31); a3 += (p3 & P31) + (p3 >> 31);
+      const u32 v = __ldg(c + ((size_t)j << LB) + t);
+      const uint4 w = *reinterpret_cast<const uint4*>(wmid + 4 * j);
+      // raw 64-bit products: four of them (< 2^62 each) plus a reduced carry-in fit, so reduce every fourth term
+      a0 += (u64)v * w.x; a1 += (u64)v * w.y; a2 += (u64)v * w.z; a3 += (u64)v * w.w;
+      if ((j & 3u) == 3u) { a0 = m31_red64(a0); a1 = m31_red64(a1); a2 = m31_red64(a2); a3 = m31_red64(a3); }
     }
-    acc = qm31_make(m31_reduce64(a0), m31_reduce64(a1), m31_reduce64(a2), m31_reduce64(a3));
+    acc = qm31_make(m31_red64(a0), m31_red64(a1), m31_red64(a2), m31_red64(a3));
     // low-bit weight of this thread
     qm31 w = qm31_one();
     for (u32 b = 0; b < LB; ++b) if ((t >> b) & 1u) w = qm31_mul(w, load_q(f + 4 * b));
@@ -98,9 +98,9 @@ nb200_status eval_at_points(nb200_ctx* ctx, const u32* coeffs, size_t n_cols, u3
   u32 nblk = 1u << (log_size - Q);
   u32 *d_fac = nullptr, *d_part = nullptr, *d_out = nullptr;
   size_t n_out = n_cols * n_points;
-  NB_CUDA(ctx, cudaMalloc(&d_fac, fac.size() * 4));
-  NB_CUDA(ctx, cudaMalloc(&d_part, n_out * nblk * 16));
-  NB_CUDA(ctx, cudaMalloc(&d_out, n_out * 16));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_fac, fac.size() * 4));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_part, n_out * nblk * 16));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_out, n_out * 16));
   NB_CUDA(ctx, cudaMemcpyAsync(d_fac, fac.data(), fac.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   dim3 grid(nblk, (u32)n_cols, (u32)n_points);
   eval_points_partial_kernel<<<grid, EP_THREADS, 0, ctx->stream>>>(coeffs, log_size, d_fac, Q, d_part, (u32)n_points);
@@ -109,7 +109,7 @@ nb200_status eval_at_points(nb200_ctx* ctx, const u32* coeffs, size_t n_cols, u3
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(ctx, cudaMemcpyAsync(out_qm31, d_out, n_out * 16, cudaMemcpyDeviceToHost, ctx->stream));
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_fac); cudaFree(d_part); cudaFree(d_out);
+  dfree(ctx, d_fac); dfree(ctx, d_part); dfree(ctx, d_out);
   return NB200_OK;
 }
 

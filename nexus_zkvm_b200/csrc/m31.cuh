@@ -37,6 +37,16 @@ NB_HD u32 m31_reduce64(u64 x) {
   u32 t = (u32)(s & P31) + (u32)(s >> 31);  // < 2^31 + 4
   return umin32(t, t - P31);
 }
+#ifdef __CUDACC__
+// device: canonical residue of any u64 in 5 instructions (2^32 == 2, 2^31 == 1 mod P): y = 2 hi + lo, then fold bit 31 and above
+__device__ __forceinline__ u32 m31_red64(u64 x) {
+  u64 y;
+  asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(y) : "r"((u32)(x >> 32)), "l"((u64)(u32)x));
+  u32 yl = (u32)y, yh = (u32)(y >> 32);
+  u32 s = (yl & P31) + __funnelshift_r(yl, yh, 31);
+  return umin32(s, s - P31);
+}
+#endif
 NB_HD u32 m31_pow(u32 a, u32 e) {
   u32 r = 1;
   while (e) { if (e & 1) r = m31_mul(r, a); a = m31_mul(a, a); e >>= 1; }

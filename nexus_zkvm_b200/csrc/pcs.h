@@ -14,7 +14,7 @@ struct QBatchDev {
   u32 coeff[4];                        // random_coeff ^ (columns in batch)
   u32 first, count;                    // entries [first, first+count)
 };
-struct QEntryDev { const u32* col; u32 c[4]; u32 pad[2]; };
+struct QEntryDev { u32 c[4]; const u32* col; u32 pad[2]; };  // 32 bytes; c first so that it loads as one 128-bit word
 
 nb200_status domain_points(nb200_ctx* ctx, u32 log_size, u32* d_x, u32* d_y);
 nb200_status quotients_launch(nb200_ctx* ctx, const QBatchDev* h_batches, size_t n_batches, const QEntryDev* h_entries, size_t n_entries,

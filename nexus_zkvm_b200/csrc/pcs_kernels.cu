@@ -62,16 +62,18 @@ __global__ void __launch_bounds__(256) quotients_kernel(const QBatchDev* __restr
   for (u32 b = 0; b < n_batches; ++b) {
     const QBatchDev* qb = batches + b;
     // numerator = sum_k c_k f_k(row) - (A y + B)
+    // sums of 64-bit products: four products (< 2^62 each) plus a reduced carry-in fit in 64 bits, so reduce every fourth entry
     u64 s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     const u32 first = qb->first, count = qb->count;
     for (u32 e = 0; e < count; ++e) {
       const QEntryDev* en = entries + first + e;
-      const u64 f = __ldg(en->col + row);
-      u64 p0 = f * en->c[0], p1 = f * en->c[1], p2 = f * en->c[2], p3 = f * en->c[3];
-      s0 += (p0 & P31) + (p0 >> 31); s1 += (p1 & P31) + (p1 >> 31);
-      s2 += (p2 & P31) + (p2 >> 31); s3 += (p3 & P31) + (p3 >> 31);
+      const u32* col = en->col;
+      const uint4 c = __ldg(reinterpret_cast<const uint4*>(en->c));
+      const u32 f = __ldg(col + row);
+      s0 += (u64)f * c.x; s1 += (u64)f * c.y; s2 += (u64)f * c.z; s3 += (u64)f * c.w;
+      if ((e & 3u) == 3u) { s0 = m31_red64(s0); s1 = m31_red64(s1); s2 = m31_red64(s2); s3 = m31_red64(s3); }
     }
-    qm31 numer = qm31_make(m31_reduce64(s0), m31_reduce64(s1), m31_reduce64(s2), m31_reduce64(s3));
+    qm31 numer = qm31_make(m31_red64(s0), m31_red64(s1), m31_red64(s2), m31_red64(s3));
     qm31 A = qm31_make(qb->A[0], qb->A[1], qb->A[2], qb->A[3]);
     qm31 B = qm31_make(qb->B[0], qb->B[1], qb->B[2], qb->B[3]);
     numer = qm31_sub(numer, qm31_add(qm31_mul_m31(A, y), B));
