@@ -38,12 +38,24 @@ __global__ void __launch_bounds__(EP_THREADS) eval_points_partial_kernel(const u
   if (t < (1u << LB)) {
     const u32* c = coeffs + ((size_t)col << log_size) + ((size_t)blk << Q);
     u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (u32 j = 0; j < nj; ++j) {
+    // raw 64-bit products: four of them (< 2^62 each) plus a reduced carry-in fit, so reduce after every fourth term; the four
+    // coefficient loads of a group are issued together
+    u32 j = 0;
+    for (; j + 4 <= nj; j += 4) {
+      const u32 v0 = __ldg(c + ((size_t)j << LB) + t), v1 = __ldg(c + ((size_t)(j + 1) << LB) + t);
+      const u32 v2 = __ldg(c + ((size_t)(j + 2) << LB) + t), v3 = __ldg(c + ((size_t)(j + 3) << LB) + t);
+      const uint4 w0 = *reinterpret_cast<const uint4*>(wmid + 4 * j), w1 = *reinterpret_cast<const uint4*>(wmid + 4 * j + 4);
+      const uint4 w2 = *reinterpret_cast<const uint4*>(wmid + 4 * j + 8), w3 = *reinterpret_cast<const uint4*>(wmid + 4 * j + 12);
+      a0 += (u64)v0 * w0.x + (u64)v1 * w1.x + (u64)v2 * w2.x + (u64)v3 * w3.x;
+      a1 += (u64)v0 * w0.y + (u64)v1 * w1.y + (u64)v2 * w2.y + (u64)v3 * w3.y;
+      a2 += (u64)v0 * w0.z + (u64)v1 * w1.z + (u64)v2 * w2.z + (u64)v3 * w3.z;
+      a3 += (u64)v0 * w0.w + (u64)v1 * w1.w + (u64)v2 * w2.w + (u64)v3 * w3.w;
+      a0 = m31_red64(a0); a1 = m31_red64(a1); a2 = m31_red64(a2); a3 = m31_red64(a3);
+    }
+    for (; j < nj; ++j) {
       const u32 v = __ldg(c + ((size_t)j << LB) + t);
       const uint4 w = *reinterpret_cast<const uint4*>(wmid + 4 * j);
-      // raw 64-bit products: four of them (< 2^62 each) plus a reduced carry-in fit, so reduce every fourth term
       a0 += (u64)v * w.x; a1 += (u64)v * w.y; a2 += (u64)v * w.z; a3 += (u64)v * w.w;
-      if ((j & 3u) == 3u) { a0 = m31_red64(a0); a1 = m31_red64(a1); a2 = m31_red64(a2); a3 = m31_red64(a3); }
     }
     acc = qm31_make(m31_red64(a0), m31_red64(a1), m31_red64(a2), m31_red64(a3));
     // low-bit weight of this thread

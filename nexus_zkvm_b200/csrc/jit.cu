@@ -180,7 +180,7 @@ std::string gen_source(const AirComponent& c) {
   // warps drift apart over the ~0.5 MB program and the kernel is instruction-fetch bound: stall_no_instruction 11 per issue).
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
     << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL) {\n"
-    << "  const u32 row = blockIdx.x * " << JIT_BLOCK << " + threadIdx.x;\n  St s;\n"
+    << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
   for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row, EL);\n  __syncthreads();\n";
   o << "  const u32 di = __ldg(dinv + (row >> " << DL << "));\n"
@@ -231,7 +231,7 @@ std::string gen_logup_source(const AirComponent& c) {
     o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.fn = fn; s.fd = fd; s.run = run;\n}\n";
   }
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 LS) {\n"
-    << "  const u32 row = blockIdx.x * " << JIT_BLOCK << " + threadIdx.x;\n  St s;\n"
+    << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n"
     << "  s.fn = Q{0u, 0u, 0u, 0u}; s.fd = Q{1u, 0u, 0u, 0u}; s.run = Q{0u, 0u, 0u, 0u};\n";
   for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, out, row, LS);\n  __syncthreads();\n";
@@ -242,6 +242,14 @@ std::string gen_logup_source(const AirComponent& c) {
 
 std::string jit_source(const AirComponent& c) { return gen_source(c); }
 std::string jit_logup_source(const AirComponent& c) { return gen_logup_source(c); }
+
+// threads per CTA at launch: the code is compiled for up to JIT_BLOCK threads at <= 64 registers; 512 runs as two CTAs per SM, which
+// measured slightly faster than one CTA of 1024 (10.7 vs 11.3 ms: the two CTAs sit in different phases of the program and share the pipes better)
+static u32 jit_block() {
+  static u32 b = 0;
+  if (!b) { b = 512; if (const char* e = getenv("NB200_JIT_BLOCK")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) b = (u32)v; } }
+  return b;
+}
 
 bool jit_enabled() {
   const char* e = getenv("NB200_JIT");
@@ -355,7 +363,7 @@ nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* co
   size_t rows = (size_t)1 << log_size;
   if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
   void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_out, (void*)&log_size};
-  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / JIT_BLOCK)), dim3(JIT_BLOCK), args, 0, ctx->stream);
+  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / jit_block())), dim3(jit_block()), args, 0, ctx->stream);
   ctx->launches += 1;
   if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));
   return NB200_OK;
@@ -368,7 +376,7 @@ nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u
   u32 el = dom_log;
   u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
   void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3, (void*)&el};
-  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / JIT_BLOCK)), dim3(JIT_BLOCK), args, 0, ctx->stream);
+  cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / jit_block())), dim3(jit_block()), args, 0, ctx->stream);
   ctx->launches += 1;
   if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));
   return NB200_OK;

@@ -7,7 +7,7 @@
 
 namespace nb {
 
-static const u32 JIT_BLOCK = 1024;       // threads per CTA of the generated kernel (one CTA per SM)
+static const u32 JIT_BLOCK = 1024;       // the generated kernels are compiled for up to this many threads per CTA (<= 64 registers)
 static const u32 JIT_MIN_INSTR = 64;      // shorter programs stay on the bytecode interpreter
 static const u32 JIT_COEFF_WORDS = 12;   // words per constraint in the coefficient table the generated kernel reads
 

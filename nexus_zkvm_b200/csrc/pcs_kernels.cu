@@ -62,16 +62,28 @@ __global__ void __launch_bounds__(256) quotients_kernel(const QBatchDev* __restr
   for (u32 b = 0; b < n_batches; ++b) {
     const QBatchDev* qb = batches + b;
     // numerator = sum_k c_k f_k(row) - (A y + B)
-    // sums of 64-bit products: four products (< 2^62 each) plus a reduced carry-in fit in 64 bits, so reduce every fourth entry
+    // sums of 64-bit products: four products (< 2^62 each) plus a reduced carry-in fit in 64 bits, so reduce after every fourth
+    // entry.  The four column loads of a group are issued before any arithmetic (the loop is otherwise latency bound: one dependent
+    // pointer + data load per entry).
     u64 s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     const u32 first = qb->first, count = qb->count;
-    for (u32 e = 0; e < count; ++e) {
-      const QEntryDev* en = entries + first + e;
-      const u32* col = en->col;
-      const uint4 c = __ldg(reinterpret_cast<const uint4*>(en->c));
-      const u32 f = __ldg(col + row);
+    const QEntryDev* en = entries + first;
+    u32 e = 0;
+    for (; e + 4 <= count; e += 4) {
+      const u32* c0p = en[e].col; const u32* c1p = en[e + 1].col; const u32* c2p = en[e + 2].col; const u32* c3p = en[e + 3].col;
+      const u32 f0 = __ldg(c0p + row), f1 = __ldg(c1p + row), f2 = __ldg(c2p + row), f3 = __ldg(c3p + row);
+      const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(en[e].c)), k1 = __ldg(reinterpret_cast<const uint4*>(en[e + 1].c));
+      const uint4 k2 = __ldg(reinterpret_cast<const uint4*>(en[e + 2].c)), k3 = __ldg(reinterpret_cast<const uint4*>(en[e + 3].c));
+      s0 += (u64)f0 * k0.x + (u64)f1 * k1.x + (u64)f2 * k2.x + (u64)f3 * k3.x;
+      s1 += (u64)f0 * k0.y + (u64)f1 * k1.y + (u64)f2 * k2.y + (u64)f3 * k3.y;
+      s2 += (u64)f0 * k0.z + (u64)f1 * k1.z + (u64)f2 * k2.z + (u64)f3 * k3.z;
+      s3 += (u64)f0 * k0.w + (u64)f1 * k1.w + (u64)f2 * k2.w + (u64)f3 * k3.w;
+      s0 = m31_red64(s0); s1 = m31_red64(s1); s2 = m31_red64(s2); s3 = m31_red64(s3);
+    }
+    for (; e < count; ++e) {   // at most three left: still within 64 bits
+      const uint4 c = __ldg(reinterpret_cast<const uint4*>(en[e].c));
+      const u32 f = __ldg(en[e].col + row);
       s0 += (u64)f * c.x; s1 += (u64)f * c.y; s2 += (u64)f * c.z; s3 += (u64)f * c.w;
-      if ((e & 3u) == 3u) { s0 = m31_red64(s0); s1 = m31_red64(s1); s2 = m31_red64(s2); s3 = m31_red64(s3); }
     }
     qm31 numer = qm31_make(m31_red64(s0), m31_red64(s1), m31_red64(s2), m31_red64(s3));
     qm31 A = qm31_make(qb->A[0], qb->A[1], qb->A[2], qb->A[3]);
@@ -87,6 +99,60 @@ __global__ void __launch_bounds__(256) quotients_kernel(const QBatchDev* __restr
   o0[row] = acc.c[0]; o1[row] = acc.c[1]; o2[row] = acc.c[2]; o3[row] = acc.c[3];
 }
 
+// Four consecutive rows per thread: every column is read with 128-bit loads (512 contiguous bytes per warp and column instead of
+// 128: the sweep jumps 2^log_size words from column to column, so longer bursts matter for DRAM efficiency) and the per-entry
+// constants are fetched once for four rows.  Same arithmetic as quotients_kernel.
+__global__ void __launch_bounds__(128) quotients_kernel_x4(const QBatchDev* __restrict__ batches, u32 n_batches, const QEntryDev* __restrict__ entries,
+                                                           const u32* __restrict__ dom_x, const u32* __restrict__ dom_y, u32 log_size,
+                                                           u32* __restrict__ o0, u32* __restrict__ o1, u32* __restrict__ o2, u32* __restrict__ o3) {
+  const u32 row = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (row >= (1u << log_size)) return;
+  const uint4 xv = __ldg(reinterpret_cast<const uint4*>(dom_x + row)), yv = __ldg(reinterpret_cast<const uint4*>(dom_y + row));
+  const u32 xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  qm31 acc[4] = {qm31_zero(), qm31_zero(), qm31_zero(), qm31_zero()};
+  for (u32 b = 0; b < n_batches; ++b) {
+    const QBatchDev* qb = batches + b;
+    u64 s[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[r][j] = 0;
+    const u32 first = qb->first, count = qb->count;
+    const QEntryDev* en = entries + first;
+    for (u32 e = 0; e < count; ++e) {
+      const uint4 f = __ldg(reinterpret_cast<const uint4*>(en[e].col + row));
+      const uint4 k = __ldg(reinterpret_cast<const uint4*>(en[e].c));
+      const u32 fr[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        s[r][0] += (u64)fr[r] * k.x; s[r][1] += (u64)fr[r] * k.y; s[r][2] += (u64)fr[r] * k.z; s[r][3] += (u64)fr[r] * k.w;
+      }
+      if ((e & 3u) == 3u) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[r][j] = m31_red64(s[r][j]);
+      }
+    }
+    const qm31 A = qm31_make(qb->A[0], qb->A[1], qb->A[2], qb->A[3]);
+    const qm31 B = qm31_make(qb->B[0], qb->B[1], qb->B[2], qb->B[3]);
+    const cm31 prx{qb->prx[0], qb->prx[1]}, pry{qb->pry[0], qb->pry[1]}, pix{qb->pix[0], qb->pix[1]}, piy{qb->piy[0], qb->piy[1]};
+    const qm31 cf = qm31_make(qb->coeff[0], qb->coeff[1], qb->coeff[2], qb->coeff[3]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      qm31 numer = qm31_make(m31_red64(s[r][0]), m31_red64(s[r][1]), m31_red64(s[r][2]), m31_red64(s[r][3]));
+      numer = qm31_sub(numer, qm31_add(qm31_mul_m31(A, ys[r]), B));
+      cm31 dx{m31_sub(prx.a, xs[r]), prx.b}, dy{m31_sub(pry.a, ys[r]), pry.b};
+      cm31 den = cm31_sub(cm31_mul(dx, piy), cm31_mul(dy, pix));
+      acc[r] = qm31_add(qm31_mul(acc[r], cf), qm31_mul_cm31(numer, cm31_inv(den)));
+    }
+  }
+  *reinterpret_cast<uint4*>(o0 + row) = make_uint4(acc[0].c[0], acc[1].c[0], acc[2].c[0], acc[3].c[0]);
+  *reinterpret_cast<uint4*>(o1 + row) = make_uint4(acc[0].c[1], acc[1].c[1], acc[2].c[1], acc[3].c[1]);
+  *reinterpret_cast<uint4*>(o2 + row) = make_uint4(acc[0].c[2], acc[1].c[2], acc[2].c[2], acc[3].c[2]);
+  *reinterpret_cast<uint4*>(o3 + row) = make_uint4(acc[0].c[3], acc[1].c[3], acc[2].c[3], acc[3].c[3]);
+}
+
 nb200_status quotients_launch(nb200_ctx* ctx, const QBatchDev* h_batches, size_t n_batches, const QEntryDev* h_entries, size_t n_entries,
                               const u32* dom_x, const u32* dom_y, u32 log_size, u32* out /* 4 columns */) {
   QBatchDev* d_b = nullptr; QEntryDev* d_e = nullptr;
@@ -95,9 +161,17 @@ nb200_status quotients_launch(nb200_ctx* ctx, const QBatchDev* h_batches, size_t
   NB_CUDA(ctx, cudaMemcpyAsync(d_b, h_batches, n_batches * sizeof(QBatchDev), cudaMemcpyHostToDevice, ctx->stream));
   NB_CUDA(ctx, cudaMemcpyAsync(d_e, h_entries, n_entries * sizeof(QEntryDev), cudaMemcpyHostToDevice, ctx->stream));
   size_t n = (size_t)1 << log_size;
-  u32 thr = 256;
-  quotients_kernel<<<(u32)((n + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
-                                                                        out, out + n, out + 2 * n, out + 3 * n);
+  bool aligned = log_size >= 2 && ((((uintptr_t)out) | ((uintptr_t)dom_x) | ((uintptr_t)dom_y)) & 15u) == 0;
+  for (size_t e = 0; e < n_entries && aligned; ++e) aligned = (((uintptr_t)h_entries[e].col) & 15u) == 0;
+  if (aligned) {
+    u32 thr = 128; size_t nt = n / 4;
+    quotients_kernel_x4<<<(u32)((nt + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
+                                                                             out, out + n, out + 2 * n, out + 3 * n);
+  } else {
+    u32 thr = 256;
+    quotients_kernel<<<(u32)((n + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
+                                                                          out, out + n, out + 2 * n, out + 3 * n);
+  }
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   dfree(ctx, d_b); dfree(ctx, d_e);
