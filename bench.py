@@ -266,11 +266,12 @@ def main():
                       "lde_fft_GBps_12B_per_elem": 12.0 * elems / (t_fft * 1e-3) / 1e9,
                       "merkle_GBps_read": (4.0 * elems * (1 << args.log_blowup)) / (t_mrk * 1e-3) / 1e9,
                       "fft_Melems_per_s": (elems * (1 + (1 << args.log_blowup))) / ((t_ifft + t_fft) * 1e-3) / 1e6}
-            roofline = {"bound": "hbm", "kernel": "fft_pass_kernel (Circle iFFT + LDE FFT, all passes)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+            roofline = {"bound": "hbm", "kernel": "fft_tile_kernel (Circle iFFT + LDE FFT: the 4 pass launches of a column batch)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak,
-                        # dram__bytes_read+write of the 4 FFT launches from profiles/ncu_fft_r01b_tile_kernel.txt (64-column
-                        # capture, 41.3 B per trace element), scaled to this step's element count
-                        "traffic": 41.3 * elems, "traffic_unit": "B per step (all FFT passes)", "algorithmic": fft_bytes,
+                        # dram__bytes_read+write of the 4 FFT launches of the 1012-column tree in profiles/ncu_fft_r01c.txt
+                        # (46.9 GB / (1012 x 2^20) = 44.2 B per trace element: two passes each for iFFT and LDE), scaled to this
+                        # step's element count
+                        "traffic": 44.2 * elems, "traffic_unit": "B per step (all FFT passes)", "algorithmic": fft_bytes,
                         "peak_source": peak_src,
                         "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
                         "time_share": {"fft": (t_ifft + t_fft) / (t_ifft + t_fft + t_mrk), "merkle": t_mrk / (t_ifft + t_fft + t_mrk)}}

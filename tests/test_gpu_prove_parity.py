@@ -139,3 +139,16 @@ def test_nvrtc_path_with_an_empty_cubin_cache(monkeypatch, tmp_path):
             ctx.close()
         assert g_proof == o_proof
     assert len(list(tmp_path.glob("*.cubin"))) >= 1
+
+
+@pytest.mark.parametrize("log_expand,blowup", [(1, 1), (3, 1), (2, 2), (3, 2), (1, 2)])
+def test_every_quotient_domain_route(backend, log_expand, blowup):
+    """Constraint quotients are evaluated on the committed LDE alone (degree bound = blow-up), on the LDE plus one half-size coset
+    (degree bound = blow-up + 1) or on the reference's full domain (anything else); all three must give the oracle's bytes."""
+    m = M.AddMachine(log_size=9, n_lanes=1, log_expand=log_expand)
+    cols, mult = m.fill_main_trace(seed=60 + log_expand)
+    cfg = dict(pow_bits=5, log_blowup=blowup, log_last=0, n_queries=3)
+    g_proof, _, _ = M.prove(m, backend, cols, mult, config=cfg)
+    o_proof, _, o_aux = M.prove(m, OracleBackend(), cols, mult, config=cfg)
+    assert g_proof == o_proof
+    verify(m, g_proof, o_aux)
