@@ -150,7 +150,47 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
   const size_t g0 = W ? (gbase | ((size_t)(s0 >> W) << lo) | (s0 & ((1u << W) - 1u))) : (gbase | s0);
   const size_t gstep = W ? ((size_t)((NT * 4) >> W) << lo) : (size_t)(NT * 4);
 
-  // ---- stage in: 128-bit coalesced global loads -> swizzled shared
+  // ---- stage in: 128-bit coalesced global loads -> swizzled shared.
+  // FUSE_TOP (forward passes whose layer count is 4k+1): the pass's top layer pairs s with s + 2^(T-1), i.e. the uint4 a thread moves at
+  // `it` with the one at `it + 2`, and its twiddle is one value per tile — so it is applied here, on the way into shared memory, instead
+  // of costing a whole shared-memory round (16 LDS + 16 STS + a barrier per thread and column) for 8 butterflies.
+  constexpr bool FUSE_TOP = !INV && REM == 1 && L > 1;
+  constexpr int NROUNDS_RUN = FUSE_TOP ? NFULL : NROUNDS;
+  if (FUSE_TOP) {
+    const u32 t2 = (NZ > 0) ? 0u : __ldg(p.tw2 + (p.tw_len - (1u << (p.tn - (lo + L - 1)))) + tile_hi);
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      if (c < (int)ncb) {
+        const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          u32 ph; size_t g;
+          if (AFFINE) { ph = phys0 + it * NT * 4; g = g0 + it * gstep; }
+          else {
+            const u32 s = (tid + it * NT) * 4;
+            ph = swz2(s);
+            g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+          }
+          u32 ph2; size_t g2;
+          if (AFFINE) { ph2 = phys0 + (it + 2) * NT * 4; g2 = g0 + (it + 2) * gstep; }
+          else {
+            const u32 s = (tid + (it + 2) * NT) * 4;
+            ph2 = swz2(s);
+            g2 = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+          }
+          uint4 a = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+          if (g < p.src_len) a = __ldg(reinterpret_cast<const uint4*>(scol + g));
+          if (NZ > 0) b4 = a;   // the partner is a zero-extension word: v0 + t*0 = v0 - t*0
+          else {
+            if (g2 < p.src_len) b4 = __ldg(reinterpret_cast<const uint4*>(scol + g2));
+            butterfly_dbl(a.x, b4.x, t2); butterfly_dbl(a.y, b4.y, t2); butterfly_dbl(a.z, b4.z, t2); butterfly_dbl(a.w, b4.w, t2);
+          }
+          *reinterpret_cast<uint4*>(sm + (c << T) + ph) = a;
+          *reinterpret_cast<uint4*>(sm + (c << T) + ph2) = b4;
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int c = 0; c < CB; ++c) {
     if (c < (int)ncb) {
@@ -170,11 +210,12 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
       }
     }
   }
+  }
   __syncthreads();
 
 #pragma unroll
-  for (int rr = 0; rr < NROUNDS; ++rr) {
-    const int ri = INV ? rr : NROUNDS - 1 - rr;
+  for (int rr = 0; rr < NROUNDS_RUN; ++rr) {
+    const int ri = INV ? rr : NROUNDS_RUN - 1 - rr;
     const int b = ri < NFULL ? W + 4 * ri : T - 4;
     const int jlo = ri < NFULL ? 0 : 4 - REM;
     const u32 tau_hi = tid >> b, tau_lo = tid & ((1u << b) - 1u);
