@@ -166,6 +166,12 @@ typedef struct nb200_scheme nb200_scheme;
 nb200_status nb200_scheme_new(nb200_ctx*, uint32_t pow_bits, uint32_t log_blowup, uint32_t log_last_layer_degree_bound,
                               uint32_t n_queries, nb200_scheme** out);
 void nb200_scheme_free(nb200_scheme*);
+/* Optional hint: log2 of the AIR's constraint degree bound relative to the trace (the reference's LOG_CONSTRAINT_DEGREE,
+ * prover/src/components/mod.rs:12; = max log_expand of the loaded AIR, nb200_air_max_log_expand).  When it equals
+ * log_blowup + 1, commits from HOST columns also evaluate the polynomials on the extra half-size coset the quotient step
+ * needs, in the shadow of the PCIe copy.  Results never depend on the hint. */
+nb200_status nb200_scheme_set_constraint_log_degree(nb200_scheme*, uint32_t log_expand);
+uint32_t nb200_air_max_log_expand(const nb200_air*);
 /* tree_builder.extend_evals(batches...); tree_builder.commit(channel)  (machine.rs:208-263): interpolate, LDE,
  * Merkle, mix_root.  The evaluation batches are only read. */
 nb200_status nb200_scheme_commit(nb200_scheme*, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel*, uint8_t root[32]);

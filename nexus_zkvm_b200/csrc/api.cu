@@ -283,7 +283,7 @@ nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t
 
 namespace nb {
 nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde) {
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext) {
   if (n_cols == 0) return NB200_OK;
   if (!ctx->copy_stream) {
     NB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -318,6 +318,8 @@ nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t 
     }
     if (st == NB200_OK) st = fft_interpolate(ctx, d_evals + c0 * len, d_coeffs + c0 * len, nc, log_size);
     if (st == NB200_OK) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_lde + c0 * lde_len, log_size + log_blowup, nc);
+    // optional: the same polynomials on the first half of the next larger canonic domain (half-domain transform, fft.cu)
+    if (st == NB200_OK && d_half_ext) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_half_ext + c0 * lde_len, log_size + log_blowup, nc, log_size + log_blowup + 1);
   }
   if (coset_order) { dfree(ctx, tmp[0]); dfree(ctx, tmp[1]); }
   return st;

@@ -112,7 +112,7 @@ nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, s
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)
 // overlaps the transforms of chunk k.  `host` is n_cols x 2^log_size words (pinned memory for real overlap).
 nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde);
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext = nullptr);
 
 struct ColRef { const u32* d; u32 log_size; };
 nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out);

@@ -27,6 +27,8 @@ namespace nb {
 
 struct SchemeTree {
   std::vector<nb200_cols*> coeffs, ldes;  // owned batches, commitment order
+  std::vector<nb200_cols*> half_ext;      // per batch or empty: the polynomials on the first half of CanonicCoset(lde log + 1).circle_domain(),
+                                          // precomputed at commit time when the scheme was told the AIR's degree bound (see component_quotients)
   struct ColLoc { u32 batch, idx, log; };
   std::vector<ColLoc> cols;               // global column index -> (batch, index in batch, polynomial log size)
   nb200_tree* merkle = nullptr;
@@ -40,6 +42,7 @@ struct nb200_scheme {
   nb200_ctx* ctx = nullptr;
   uint32_t pow_bits = 5, log_blowup = 1, log_last = 0, n_queries = 3;  // PcsConfig::default() [risk A.4]
   std::vector<nb::SchemeTree> trees;
+  uint32_t hint_log_expand = 0;  // nb200_scheme_set_constraint_log_degree: 0 = unknown
 };
 
 extern "C" nb200_status nb200_cols_alloc(nb200_ctx*, size_t, uint32_t, nb200_cols**);
@@ -59,6 +62,7 @@ struct ColsGuard {
 static void free_tree(nb200_ctx* ctx, SchemeTree& t) {
   for (auto* c : t.coeffs) nb200_cols_free(ctx, c);
   for (auto* c : t.ldes) nb200_cols_free(ctx, c);
+  for (auto* c : t.half_ext) if (c) nb200_cols_free(ctx, c);
   if (t.merkle) nb200_tree_free(ctx, t.merkle);
   t = SchemeTree();
 }
@@ -120,7 +124,16 @@ nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const s
     t.coeffs.push_back(co);
     NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + s->log_blowup, &lde));
     t.ldes.push_back(lde);
-    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d));
+    // The copy from the host is PCIe-bound and leaves the SMs mostly idle: if the AIR's degree bound is known to need the half-coset
+    // evaluations of these polynomials later (component_quotients, Q_HALF), compute them now, chunk by chunk, in that shadow.
+    nb200_cols* hx = nullptr;
+    const u32 lde_log = log_sizes[b] + s->log_blowup;
+    if (s->hint_log_expand == s->log_blowup + 1 && lde_log > 8) {
+      NB_TRY(twiddles_prepare(ctx, lde_log + 1));
+      NB_TRY(nb200_cols_alloc(ctx, n_cols[b], lde_log, &hx));
+    }
+    t.half_ext.push_back(hx);
+    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d, hx ? hx->d : nullptr));
   }
   trace_mark(ctx, "commit(host): h2d+ifft+lde");
   nb200_status st = finish_tree(ctx, t, ch);
@@ -280,6 +293,10 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
     mask_lde[m] = s->trees[mk.tree].ldes[loc.batch]->col(loc.idx);
     if (reuse_lde) { mask_cols[m] = mask_lde[m]; continue; }
     auto key = std::make_pair(mk.tree, loc.batch);
+    if (mode == Q_HALF && loc.batch < s->trees[mk.tree].half_ext.size() && s->trees[mk.tree].half_ext[loc.batch]) {
+      mask_cols[m] = s->trees[mk.tree].half_ext[loc.batch]->col(loc.idx);   // precomputed at commit time
+      continue;
+    }
     if (!ext.count(key)) {
       const nb200_cols* co = s->trees[mk.tree].coeffs[loc.batch];
       nb200_cols* e = nullptr;
@@ -792,6 +809,16 @@ nb200_status nb200_scheme_new(nb200_ctx* ctx, uint32_t pow_bits, uint32_t log_bl
   s->ctx = ctx; s->pow_bits = pow_bits; s->log_blowup = log_blowup; s->log_last = log_last_layer_degree_bound; s->n_queries = n_queries;
   *out = s;
   return NB200_OK;
+}
+nb200_status nb200_scheme_set_constraint_log_degree(nb200_scheme* s, uint32_t log_expand) {
+  if (!s) return NB200_ERR_ARG;
+  s->hint_log_expand = log_expand;
+  return NB200_OK;
+}
+uint32_t nb200_air_max_log_expand(const nb200_air* a) {
+  uint32_t m = 0;
+  if (a) for (auto& c : a->prog.comps) m = std::max<uint32_t>(m, c.log_expand);
+  return m;
 }
 void nb200_scheme_free(nb200_scheme* s) {
   if (!s) return;

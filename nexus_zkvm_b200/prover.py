@@ -83,6 +83,9 @@ class CommitmentSchemeProver:
         self._h = C.c_void_p()
         ctx._chk(lib().nb200_scheme_new(ctx._h, C.c_uint32(config["pow_bits"]), C.c_uint32(config["log_blowup"]),
                                         C.c_uint32(config["log_last"]), C.c_uint32(config["n_queries"]), C.byref(self._h)))
+        lib().nb200_air_max_log_expand.restype = C.c_uint32
+        lib().nb200_air_max_log_expand.argtypes = [C.c_void_p]
+        ctx._chk(lib().nb200_scheme_set_constraint_log_degree(self._h, C.c_uint32(lib().nb200_air_max_log_expand(self.air._h))))
         self.tree_evals = []  # per committed tree: list of eval batches (kept alive; read by gen_interaction)
 
     def __del__(self):
