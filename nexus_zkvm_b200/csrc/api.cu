@@ -141,13 +141,13 @@ nb200_status nb200_cols_upload(nb200_ctx* ctx, nb200_cols* c, size_t first, size
     return NB200_OK;
   }
   u32* tmp = nullptr;
-  NB_CUDA(ctx, cudaMalloc(&tmp, bytes));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp, bytes));
   cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   nb200_status st = NB200_OK;
   if (e != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e));
   if (st == NB200_OK) st = reorder_coset_to_bitrev(ctx, tmp, c->col(first), n, c->log_size);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(tmp);
+  dfree(ctx, tmp);
   return st;
 }
 nb200_status nb200_cols_download(nb200_ctx* ctx, const nb200_cols* c, size_t first, size_t n, uint32_t* host) {
@@ -163,11 +163,11 @@ nb200_status nb200_cols_finalize_order(nb200_ctx* ctx, nb200_cols* c) {
   size_t bytes = (c->n_cols << c->log_size) * 4;
   if (!bytes) return NB200_OK;
   u32* tmp = nullptr;
-  NB_CUDA(ctx, cudaMalloc(&tmp, bytes));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp, bytes));
   cudaError_t e = cudaMemcpyAsync(tmp, c->d, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
   nb200_status st = e == cudaSuccess ? reorder_coset_to_bitrev(ctx, tmp, c->d, c->n_cols, c->log_size) : set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e));
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(tmp);
+  dfree(ctx, tmp);
   return st;
 }
 

@@ -175,9 +175,9 @@ std::string gen_source(const AirComponent& c) {
     }
     o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.rr = rr;\n}\n";
   }
-  // One CTA of JIT_BLOCK threads per SM, re-converged after every chunk: all warps of an SM then execute the same few tens
-  // of KB of straight-line code at a time, so the instruction cache serves them from one fetch (without the barriers the
-  // warps drift apart over the ~0.5 MB program and the kernel is instruction-fetch bound: stall_no_instruction 11 per issue).
+  // The CTAs re-converge (__syncthreads) after every chunk: the warps of a CTA then execute the same few tens of KB of straight-line
+  // code at a time and the instruction cache serves them from one fetch.  Without the barriers the warps drift apart over the ~0.7 MB
+  // program and the kernel is instruction-fetch bound (ncu: stall_no_instruction 11 per issue, icc hit rate 53 %).
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
     << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL) {\n"
     << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"

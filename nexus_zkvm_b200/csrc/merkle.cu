@@ -71,6 +71,35 @@ __global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restri
   o[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// The last layers of a tree (no more columns to inject, <= 2^TAIL_LOG nodes) in ONE launch: a single CTA walks them with a barrier
+// per layer.  A proof commits ~25 trees (4 trace trees + one per FRI layer); their small layers are pure launch latency otherwise.
+static constexpr u32 TAIL_LOG = 9;
+template <int VARIANT>
+__global__ void __launch_bounds__(256) merkle_tail_kernel(uint4* __restrict__ pool, u32 top_log, const u32 one) {
+  for (int l = (int)top_log; l >= 0; --l) {
+    const uint4* prev = pool + 2 * (((size_t)1 << (l + 1)) - 1);   // layer l + 1 (written by the previous launch or iteration)
+    uint4* outl = pool + 2 * (((size_t)1 << l) - 1);
+    for (u32 row = threadIdx.x; row < (1u << l); row += blockDim.x) {
+      u32 h[8], m[16];
+      const uint4* p = prev + 4 * row;
+      uint4 a = p[0], b = p[1], c = p[2], d = p[3];                 // plain loads: the data may come from this very kernel
+      m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+      m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+      if (VARIANT == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = 0;
+        b2s_compress_fma(h, m, 0, 0, 0, 0, one);
+      } else {
+        b2s_init(h);
+        b2s_compress_fma(h, m, 64u, 0, 0xFFFFFFFFu, 0, one);
+      }
+      outl[2 * row] = make_uint4(h[0], h[1], h[2], h[3]);
+      outl[2 * row + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    __syncthreads();
+  }
+}
+
 nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, nb200_tree** out) {
   // stable sort by length, descending (MerkleProver::commit)
   std::vector<ColRef> cols = cols_in;
@@ -103,6 +132,13 @@ nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, n
     size_t first = ci;
     while (ci < cols.size() && cols[ci].log_size == (u32)l) ++ci;
     u32 n_here = (u32)(ci - first);
+    if (n_here == 0 && ci == cols.size() && l < (int)max_log && l <= (int)TAIL_LOG) {
+      // nothing but inner nodes from here to the root
+      if (ctx->merkle_hash == 0) merkle_tail_kernel<0><<<1, 256, 0, ctx->stream>>>((uint4*)tree->d_pool, (u32)l, 1u);
+      else merkle_tail_kernel<1><<<1, 256, 0, ctx->stream>>>((uint4*)tree->d_pool, (u32)l, 1u);
+      ctx->launches += 1;
+      break;
+    }
     const uint4* prev = (l == (int)max_log) ? nullptr : (const uint4*)tree->layer[l + 1];
     size_t rows = (size_t)1 << l;
     u32 threads = 128;
@@ -135,27 +171,27 @@ __global__ void gather_hash_kernel(const uint4* const* __restrict__ addrs, size_
 nb200_status gather_u32(nb200_ctx* ctx, const std::vector<const u32*>& addrs, u32* host_out) {
   if (addrs.empty()) return NB200_OK;
   const u32** d_a = nullptr; u32* d_o = nullptr;
-  NB_CUDA(ctx, cudaMalloc(&d_a, addrs.size() * sizeof(u32*)));
-  NB_CUDA(ctx, cudaMalloc(&d_o, addrs.size() * 4));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_a, addrs.size() * sizeof(u32*)));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_o, addrs.size() * 4));
   NB_CUDA(ctx, cudaMemcpyAsync(d_a, addrs.data(), addrs.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
   gather_u32_kernel<<<(u32)((addrs.size() + 255) / 256), 256, 0, ctx->stream>>>(d_a, addrs.size(), d_o);
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(ctx, cudaMemcpyAsync(host_out, d_o, addrs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_a); cudaFree(d_o);
+  dfree(ctx, (void*)d_a); dfree(ctx, (void*)d_o);
   return NB200_OK;
 }
 nb200_status gather_hash(nb200_ctx* ctx, const std::vector<const uint8_t*>& addrs, uint8_t* host_out) {
   if (addrs.empty()) return NB200_OK;
   const uint4** d_a = nullptr; uint4* d_o = nullptr;
-  NB_CUDA(ctx, cudaMalloc(&d_a, addrs.size() * sizeof(void*)));
-  NB_CUDA(ctx, cudaMalloc(&d_o, addrs.size() * 32));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_a, addrs.size() * sizeof(void*)));
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_o, addrs.size() * 32));
   NB_CUDA(ctx, cudaMemcpyAsync(d_a, addrs.data(), addrs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   gather_hash_kernel<<<(u32)((addrs.size() + 255) / 256), 256, 0, ctx->stream>>>(d_a, addrs.size(), d_o);
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(ctx, cudaMemcpyAsync(host_out, d_o, addrs.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_a); cudaFree(d_o);
+  dfree(ctx, (void*)d_a); dfree(ctx, (void*)d_o);
   return NB200_OK;
 }
 

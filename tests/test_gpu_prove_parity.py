@@ -152,3 +152,26 @@ def test_every_quotient_domain_route(backend, log_expand, blowup):
     o_proof, _, o_aux = M.prove(m, OracleBackend(), cols, mult, config=cfg)
     assert g_proof == o_proof
     verify(m, g_proof, o_aux)
+
+
+def test_degree_hint_only_moves_work(backend):
+    """nb200_scheme_set_constraint_log_degree lets host commits pre-compute the half-coset evaluations under the PCIe copy; the
+    proof must not depend on it (0 = unknown, a wrong value, the right value)."""
+    import ctypes as C
+    m = M.AddMachine(log_size=9, n_lanes=2)
+    cols, mult = m.fill_main_trace(seed=8)
+    o_proof, _, _ = M.prove(m, OracleBackend(), cols, mult)
+
+    class Hinted(CudaBackend):
+        def __init__(self, ctx, hint):
+            super().__init__(ctx)
+            self.hint = hint
+
+        def prover(self, words, config):
+            p = super().prover(words, config)
+            self.ctx._chk(nb.lib().nb200_scheme_set_constraint_log_degree(p._h, C.c_uint32(self.hint)))
+            return p
+
+    for hint in (0, 1, 2, 5):
+        g_proof, _, _ = M.prove(m, Hinted(backend.ctx, hint), cols, mult)
+        assert g_proof == o_proof, f"hint {hint}"
