@@ -33,7 +33,7 @@ TREE_COLS = (27, 347, 1012)  # preprocessed+program, main, interaction (SURVEY.m
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
@@ -50,16 +50,46 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a thread every few ms
+    (a 5-step timed region lasts ~0.15 s, too short for `nvidia-smi -lms`); nvidia-smi is the fallback when pynvml is unusable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0):
-        self.index = index
-        self.rows = []
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.rows = []          # nvidia-smi rows
+        self.samples = []       # (sm_mhz, reasons bitmask) from NVML
         self.proc = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                u = self.uuid if str(self.uuid).startswith("GPU-") else "GPU-" + str(self.uuid)
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u.encode() if hasattr(u, "encode") else u)
+            except Exception:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis:
+            ent = vis.split(",")
+            if self.index < len(ent) and ent[self.index].strip().isdigit():
+                idx = int(ent[self.index])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.max_mhz = int(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -68,11 +98,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=1)
+            sm = sorted(m for m, _ in self.samples)
+            reasons = set()
+            for _, rs in self.samples:
+                for bit, name in self.NVML_REASONS.items():
+                    if rs & bit:
+                        reasons.add(name)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +145,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(nme)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def synth_trace_torch(torch, dev, log_rows, tree_cols, seed):
@@ -212,7 +267,7 @@ def main():
         for _ in range(args.warmup):
             roots = step()
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if rank == 0 else None
         if sampler:
             sampler.start()
         l0 = ctx.launches
