@@ -368,7 +368,7 @@ def main():
             if world > 1:
                 dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             e2e = {"value": world * n_rows / (float(ems.item()) / args.e2e_steps * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32 * len(tree_cols), "steps": args.e2e_steps}
+                   "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 32 * len(tree_cols) * world, "steps": args.e2e_steps}  # whole job
             del host
 
     full_prove = None
