@@ -63,3 +63,21 @@ def test_kernel_sources_and_cache_keys_without_a_gpu():
     keys = [k for k, _ in a + b]
     assert len(set(keys)) == len(keys)
     assert [k for k, _ in B.kernel_sources(M.AddMachine(log_size=8, n_lanes=1).words)] == [k for k, _ in a]
+
+
+def test_native_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/prove_demo.cc compiles against include/nb200.h, links against the library, and — on a machine without a CUDA
+    device — stops at nb200_ctx_create instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    from nexus_zkvm_b200 import machine as M
+    from tests.native_job import build_demo, write_job
+    exe = build_demo()
+    if torch.cuda.is_available():
+        return  # the GPU variant of this test (tests/test_gpu_native_host.py) covers the success path
+    m = M.AddMachine(log_size=8, n_lanes=1)
+    cols, mult = m.fill_main_trace(seed=1)
+    write_job(tmp_path / "job.bin", m, cols, mult, dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3))
+    r = subprocess.run([exe, str(tmp_path / "job.bin"), str(tmp_path / "proof.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no context" in r.stderr
+    assert not (tmp_path / "proof.bin").exists()
