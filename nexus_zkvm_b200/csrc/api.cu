@@ -282,8 +282,16 @@ nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t
 }  // extern "C" (reopened below)
 
 namespace nb {
+// index of the batch whose columns alone form the leaf layer of the tree (the only batch of the maximal size), or -1
+long leaf_sink_batch(const size_t* n_cols, const u32* log_sizes, size_t n_batches) {
+  u32 mx = 0; long idx = -1; size_t count = 0;
+  for (size_t b = 0; b < n_batches; ++b) if (n_cols[b] && log_sizes[b] > mx) mx = log_sizes[b];
+  for (size_t b = 0; b < n_batches; ++b) if (n_cols[b] && log_sizes[b] == mx) { idx = (long)b; ++count; }
+  return count == 1 ? idx : -1;
+}
+
 nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext) {
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext, LeafSink* leaf) {
   if (n_cols == 0) return NB200_OK;
   if (!ctx->copy_stream) {
     NB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -296,6 +304,7 @@ nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t 
   // ~256 MiB chunks, multiples of 4 columns (the FFT kernels batch 4 columns per CTA)
   size_t chunk = std::max<size_t>(4, ((size_t)64 << 20) / len);
   chunk = (chunk + 3) & ~(size_t)3;
+  if (leaf && leaf->tree) chunk = (chunk + 15) & ~(size_t)15;   // whole 16-column Blake2s message blocks per chunk
   if (chunk > n_cols) chunk = n_cols;
   u32* tmp[2] = {nullptr, nullptr};
   if (coset_order) for (int i = 0; i < 2; ++i) NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp[i], chunk * len * 4));
@@ -320,6 +329,8 @@ nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t 
     if (st == NB200_OK) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_lde + c0 * lde_len, log_size + log_blowup, nc);
     // optional: the same polynomials on the first half of the next larger canonic domain (half-domain transform, fft.cu)
     if (st == NB200_OK && d_half_ext) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_half_ext + c0 * lde_len, log_size + log_blowup, nc, log_size + log_blowup + 1);
+    // optional: continue the Merkle leaf hashes over this chunk's LDE columns
+    if (st == NB200_OK && leaf && leaf->tree) st = merkle_leaf_absorb(ctx, leaf->tree, d_lde + c0 * lde_len, lde_len, nc, c0, n_cols, c0 + nc == n_cols);
   }
   if (coset_order) { dfree(ctx, tmp[0]); dfree(ctx, tmp[1]); }
   return st;
@@ -343,6 +354,9 @@ nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batch
   for (size_t b = 0; b < n_batches; ++b) max_log = std::max(max_log, log_sizes[b] + log_blowup);
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
   std::vector<ColRef> cols;
+  LeafSink sink;
+  const long leaf_batch = leaf_sink_batch(n_cols, log_sizes, n_batches);
+  if (leaf_batch >= 0) NB_TRY(merkle_tree_alloc(ctx, max_log, &sink.tree));
   for (size_t b = 0; b < n_batches; ++b) {
     if (!evals_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &evals_io[b]));
     if (!coeffs_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &coeffs_io[b]));
@@ -350,10 +364,11 @@ nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batch
     NB_ARG(ctx, evals_io[b]->n_cols == n_cols[b] && evals_io[b]->log_size == log_sizes[b] && coeffs_io[b]->n_cols == n_cols[b] &&
                     coeffs_io[b]->log_size == log_sizes[b] && lde_io[b]->n_cols == n_cols[b] && lde_io[b]->log_size == log_sizes[b] + log_blowup,
            "commit_host: batch shapes");
-    NB_TRY(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d));
+    NB_TRY(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d,
+                                      nullptr, (long)b == leaf_batch ? &sink : nullptr));
     for (size_t c = 0; c < n_cols[b]; ++c) cols.push_back(ColRef{lde_io[b]->col(c), lde_io[b]->log_size});
   }
-  NB_TRY(merkle_commit(ctx, cols, tree_out));
+  NB_TRY(merkle_commit(ctx, cols, tree_out, sink.tree));
   if (root) memcpy(root, (*tree_out)->root, 32);
   return NB200_OK;
 }

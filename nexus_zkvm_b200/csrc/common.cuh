@@ -111,10 +111,15 @@ nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst,
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)
 // overlaps the transforms of chunk k.  `host` is n_cols x 2^log_size words (pinned memory for real overlap).
+struct LeafSink { nb200_tree* tree = nullptr; };  // set for the one batch that holds all the largest columns of a tree (incremental leaf hashing)
 nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext = nullptr);
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext = nullptr, LeafSink* leaf = nullptr);
 
 struct ColRef { const u32* d; u32 log_size; };
-nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out);
+nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out, nb200_tree* pre_leaf = nullptr);
+// incremental leaf hashing while column chunks arrive from the host (merkle.cu)
+nb200_status merkle_tree_alloc(nb200_ctx* ctx, u32 max_log, nb200_tree** out);
+nb200_status merkle_leaf_absorb(nb200_ctx* ctx, nb200_tree* tree, const u32* d_cols, size_t stride, size_t n_cols, size_t cols_before, size_t total_cols, bool final);
+long leaf_sink_batch(const size_t* n_cols, const u32* log_sizes, size_t n_batches);  // set for the one batch that holds all the largest columns of a tree
 
 }  // namespace nb

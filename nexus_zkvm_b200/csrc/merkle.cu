@@ -71,6 +71,78 @@ __global__ void __launch_bounds__(128) merkle_layer_kernel(const uint4* __restri
   o[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// Incremental leaf hashing: the largest columns of a tree arrive from the host in chunks (commitment order, whole 16-column message
+// blocks); each chunk continues the per-row Blake2s state kept in the tree's leaf layer, so that when the last chunk has been
+// transformed only the inner layers are left.  The work hides in the shadow of the PCIe copy of the next chunk (api.cu).
+// Same bytes as merkle_layer_kernel with prev == nullptr over all the columns at once.
+template <int VARIANT>
+__global__ void __launch_bounds__(128) merkle_leaf_absorb_kernel(uint4* __restrict__ state, const u32* __restrict__ cols, size_t stride, u32 n_cols,
+                                                                 u32 log_size, u64 bytes_before, u64 total_bytes, int first, int final, const u32 one) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= ((size_t)1 << log_size)) return;
+  u32 h[8], m[16];
+  uint4* st = state + 2 * row;
+  if (first) {
+    if (VARIANT == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = 0;
+    } else {
+      b2s_init(h);
+    }
+  } else {
+    uint4 a = st[0], b = st[1];
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+  }
+  for (u32 c0 = 0; c0 < n_cols; c0 += 16) {
+    if (c0 + 16 <= n_cols) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m[j] = __ldg(cols + (size_t)(c0 + j) * stride + row);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m[j] = (c0 + j < n_cols) ? __ldg(cols + (size_t)(c0 + j) * stride + row) : 0u;
+    }
+    if (VARIANT == 0) {
+      b2s_compress_fma(h, m, 0, 0, 0, 0, one);
+    } else {
+      const bool last = final && (c0 + 16 >= n_cols);
+      const u64 t = last ? total_bytes : bytes_before + (u64)(c0 + 16) * 4;
+      b2s_compress_fma(h, m, (u32)t, (u32)(t >> 32), last ? 0xFFFFFFFFu : 0u, 0, one);
+    }
+  }
+  st[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  st[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+static nb200_status tree_alloc(nb200_ctx* ctx, u32 max_log, nb200_tree** out) {
+  NB_ARG(ctx, max_log <= 30, "merkle: column too large");
+  nb200_tree* tree = new nb200_tree();
+  tree->ctx = ctx;
+  tree->max_log = max_log;
+  size_t total_nodes = ((size_t)2 << max_log) - 1;
+  cudaError_t e = dmalloc(ctx, (void**)&tree->d_pool, total_nodes * 32);
+  if (e != cudaSuccess) { delete tree; return set_err(ctx, NB200_ERR_OOM, std::string("merkle pool: ") + cudaGetErrorString(e)); }
+  tree->layer.resize(max_log + 1);
+  size_t off = 0;
+  for (u32 l = 0; l <= max_log; ++l) { tree->layer[l] = tree->d_pool + off * 32; off += (size_t)1 << l; }
+  *out = tree;
+  return NB200_OK;
+}
+nb200_status merkle_tree_alloc(nb200_ctx* ctx, u32 max_log, nb200_tree** out) { return tree_alloc(ctx, max_log, out); }
+
+// absorb columns [cols_before, cols_before + n_cols) of the tree's `total_cols` leaf-level columns; n_cols must be a multiple of 16 unless final
+nb200_status merkle_leaf_absorb(nb200_ctx* ctx, nb200_tree* tree, const u32* d_cols, size_t stride, size_t n_cols, size_t cols_before, size_t total_cols, bool final) {
+  NB_ARG(ctx, tree && n_cols > 0 && cols_before % 16 == 0 && (final || n_cols % 16 == 0) && cols_before + n_cols <= total_cols, "merkle_leaf_absorb: chunking");
+  const size_t rows = (size_t)1 << tree->max_log;
+  const u32 threads = 128, blocks = (u32)((rows + threads - 1) / threads);
+  uint4* st = (uint4*)tree->layer[tree->max_log];
+  if (ctx->merkle_hash == 0)
+    merkle_leaf_absorb_kernel<0><<<blocks, threads, 0, ctx->stream>>>(st, d_cols, stride, (u32)n_cols, tree->max_log, (u64)cols_before * 4, (u64)total_cols * 4, cols_before == 0, final, 1u);
+  else
+    merkle_leaf_absorb_kernel<1><<<blocks, threads, 0, ctx->stream>>>(st, d_cols, stride, (u32)n_cols, tree->max_log, (u64)cols_before * 4, (u64)total_cols * 4, cols_before == 0, final, 1u);
+  NB_LAUNCH_CHECK(ctx);
+  return NB200_OK;
+}
+
 // The last layers of a tree (no more columns to inject, <= 2^TAIL_LOG nodes) in ONE launch: a single CTA walks them with a barrier
 // per layer.  A proof commits ~25 trees (4 trace trees + one per FRI layer); their small layers are pure launch latency otherwise.
 static constexpr u32 TAIL_LOG = 9;
@@ -100,22 +172,19 @@ __global__ void __launch_bounds__(256) merkle_tail_kernel(uint4* __restrict__ po
   }
 }
 
-nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, nb200_tree** out) {
+// pre_leaf: a tree from merkle_tree_alloc whose leaf layer already holds the hashes of ALL the largest columns (merkle_leaf_absorb);
+// it is consumed (becomes *out, or is freed on failure)
+nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, nb200_tree** out, nb200_tree* pre_leaf) {
   // stable sort by length, descending (MerkleProver::commit)
   std::vector<ColRef> cols = cols_in;
   std::stable_sort(cols.begin(), cols.end(), [](const ColRef& a, const ColRef& b) { return a.log_size > b.log_size; });
   u32 max_log = cols.empty() ? 0 : cols[0].log_size;
-  NB_ARG(ctx, max_log <= 30, "merkle: column too large");
-  nb200_tree* tree = new nb200_tree();
-  tree->ctx = ctx;
-  tree->max_log = max_log;
-  size_t total_nodes = ((size_t)2 << max_log) - 1;
-  cudaError_t e = dmalloc(ctx, (void**)&tree->d_pool, total_nodes * 32);
-  if (e != cudaSuccess) { delete tree; return set_err(ctx, NB200_ERR_OOM, std::string("merkle pool: ") + cudaGetErrorString(e)); }
-  tree->layer.resize(max_log + 1);
-  {
-    size_t off = 0;
-    for (u32 l = 0; l <= max_log; ++l) { tree->layer[l] = tree->d_pool + off * 32; off += (size_t)1 << l; }
+  nb200_tree* tree = pre_leaf;
+  cudaError_t e = cudaSuccess;
+  if (tree) {
+    if (tree->max_log != max_log) { dfree(ctx, tree->d_pool); delete tree; return set_err(ctx, NB200_ERR_ARG, "merkle: precomputed leaf layer of the wrong size"); }
+  } else {
+    NB_TRY(tree_alloc(ctx, max_log, &tree));
   }
   // device array of column pointers in sorted order
   const u32** d_ptrs = nullptr;
@@ -128,7 +197,12 @@ nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols_in, n
     if (e != cudaSuccess) { dfree(ctx, (void*)d_ptrs); dfree(ctx, tree->d_pool); delete tree; return set_err(ctx, NB200_ERR_CUDA, cudaGetErrorString(e)); }
   }
   size_t ci = 0;
-  for (int l = (int)max_log; l >= 0; --l) {
+  int l_start = (int)max_log;
+  if (pre_leaf) {  // the leaf layer is done: skip its columns
+    while (ci < cols.size() && cols[ci].log_size == max_log) ++ci;
+    l_start = (int)max_log - 1;
+  }
+  for (int l = l_start; l >= 0; --l) {
     size_t first = ci;
     while (ci < cols.size() && cols[ci].log_size == (u32)l) ++ci;
     u32 n_here = (u32)(ci - first);

@@ -67,7 +67,7 @@ static void free_tree(nb200_ctx* ctx, SchemeTree& t) {
   t = SchemeTree();
 }
 
-static nb200_status finish_tree(nb200_ctx* ctx, SchemeTree& t, HostChannel& ch) {
+static nb200_status finish_tree(nb200_ctx* ctx, SchemeTree& t, HostChannel& ch, nb200_tree* pre_leaf = nullptr) {
   std::vector<ColRef> refs;
   t.cols.clear();
   for (size_t b = 0; b < t.ldes.size(); ++b)
@@ -75,7 +75,7 @@ static nb200_status finish_tree(nb200_ctx* ctx, SchemeTree& t, HostChannel& ch) 
       refs.push_back(ColRef{t.ldes[b]->col(c), t.ldes[b]->log_size});
       t.cols.push_back(SchemeTree::ColLoc{(u32)b, (u32)c, t.coeffs[b]->log_size});
     }
-  NB_TRY(merkle_commit(ctx, refs, &t.merkle));
+  NB_TRY(merkle_commit(ctx, refs, &t.merkle, pre_leaf));
   ch.mix_root(t.merkle->root);
   return NB200_OK;
 }
@@ -116,6 +116,10 @@ nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const s
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
   trace_mark(ctx, nullptr);
   SchemeTree t;
+  // leaf hashes are continued chunk by chunk under the PCIe copy when one batch holds all the largest columns
+  LeafSink sink;
+  const long leaf_batch = leaf_sink_batch(n_cols, log_sizes, n);
+  if (leaf_batch >= 0) NB_TRY(merkle_tree_alloc(ctx, max_log, &sink.tree));
   for (size_t b = 0; b < n; ++b) {
     nb200_cols *ev = nullptr, *co = nullptr, *lde = nullptr;
     NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &ev));
@@ -133,10 +137,11 @@ nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const s
       NB_TRY(nb200_cols_alloc(ctx, n_cols[b], lde_log, &hx));
     }
     t.half_ext.push_back(hx);
-    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d, hx ? hx->d : nullptr));
+    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d, hx ? hx->d : nullptr,
+                                      (long)b == leaf_batch ? &sink : nullptr));
   }
   trace_mark(ctx, "commit(host): h2d+ifft+lde");
-  nb200_status st = finish_tree(ctx, t, ch);
+  nb200_status st = finish_tree(ctx, t, ch, sink.tree);
   if (st != NB200_OK) { free_tree(ctx, t); return st; }
   trace_mark(ctx, "commit: merkle");
   if (root) memcpy(root, t.merkle->root, 32);
