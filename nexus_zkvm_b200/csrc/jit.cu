@@ -206,14 +206,38 @@ std::string gen_logup_source(const AirComponent& c) {
   };
   size_t CH = 150;
   size_t n_chunks = (c.logup_prog.size() + CH - 1) / CH;
+  // The QM31 inverse (one per batch of fractions; 38 M31 products for x^(P-2) alone) is batched over G consecutive batches of the same
+  // row: prefix products, ONE inverse, back-substitution (3 products per extra batch).  The inverse is unique, so the values are the
+  // interpreter's.  `pending` batches wait in pfn/pfd until the group is full; the running row sum is then advanced batch by batch.
+  const int G = 4;
   u32 k = 0; bool have = false; u32 cur_batch = 0;
-  auto finalize = [&](std::ostringstream& o2) {
-    o2 << "  run = qadd(run, qmul(fn, qinv(fd)));\n";
-    for (int cc = 0; cc < 4; ++cc) o2 << "  out[(" << (4 * (size_t)cur_batch + cc) << "ull << LS) + row] = run.c" << cc << ";\n";
+  std::vector<u32> pending;   // batch ids waiting in slots 0..pending.size()-1 (tracked at code-generation time)
+  auto flush = [&](std::ostringstream& o2) {
+    const int n = (int)pending.size();
+    if (n == 0) return;
+    o2 << "  {\n";
+    for (int g = 1; g < n; ++g) o2 << "    Q pp" << g << " = qmul(" << (g == 1 ? std::string("pfd0") : "pp" + std::to_string(g - 1)) << ", pfd" << g << ");\n";
+    o2 << "    Q iv = qinv(" << (n == 1 ? std::string("pfd0") : "pp" + std::to_string(n - 1)) << ");\n";
+    for (int g = n - 1; g >= 1; --g)
+      o2 << "    { Q t = qmul(iv, " << (g == 1 ? std::string("pfd0") : "pp" + std::to_string(g - 1)) << "); iv = qmul(iv, pfd" << g << "); pfd" << g << " = t; }\n";
+    o2 << "    pfd0 = iv;\n";
+    for (int g = 0; g < n; ++g) {
+      o2 << "    run = qadd(run, qmul(pfn" << g << ", pfd" << g << "));\n";
+      for (int cc = 0; cc < 4; ++cc) o2 << "    out[(" << (4 * (size_t)pending[g] + cc) << "ull << LS) + row] = run.c" << cc << ";\n";
+    }
+    o2 << "  }\n";
+    pending.clear();
   };
+  auto finalize = [&](std::ostringstream& o2) {   // the current batch's combined fraction fn / fd is complete
+    o2 << "  pfn" << pending.size() << " = fn; pfd" << pending.size() << " = fd;\n";
+    pending.push_back(cur_batch);
+    if ((int)pending.size() == G) flush(o2);
+  };
+  o << "struct Pend { Q n[" << G << "], d[" << G << "]; };\n";
   for (size_t ci = 0; ci < n_chunks; ++ci) {
-    o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 row, u32 LS) {\n";
+    o << "__device__ __noinline__ void chunk" << ci << "(St& s, Pend& pe, const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 row, u32 LS) {\n";
     o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q fn = s.fn, fd = s.fd, run = s.run;\n";
+    for (int g = 0; g < G; ++g) o << "  Q pfn" << g << " = pe.n[" << g << "], pfd" << g << " = pe.d[" << g << "];\n";
     o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
     for (size_t pc = ci * CH; pc < std::min(c.logup_prog.size(), (ci + 1) * CH); ++pc) {
       const AirInstr& in = c.logup_prog[pc];
@@ -227,14 +251,17 @@ std::string gen_logup_source(const AirComponent& c) {
         o << "  "; emit_op(o, in, ld); o << "\n";
       }
     }
-    if (ci + 1 == n_chunks && have) finalize(o);
-    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.fn = fn; s.fd = fd; s.run = run;\n}\n";
+    if (ci + 1 == n_chunks) { if (have) finalize(o); flush(o); }
+    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.fn = fn; s.fd = fd; s.run = run;\n";
+    for (int g = 0; g < G; ++g) o << "  pe.n[" << g << "] = pfn" << g << "; pe.d[" << g << "] = pfd" << g << ";\n";
+    o << "}\n";
   }
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 LS) {\n"
     << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n"
-    << "  s.fn = Q{0u, 0u, 0u, 0u}; s.fd = Q{1u, 0u, 0u, 0u}; s.run = Q{0u, 0u, 0u, 0u};\n";
-  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, out, row, LS);\n  __syncthreads();\n";
+    << "  s.fn = Q{0u, 0u, 0u, 0u}; s.fd = Q{1u, 0u, 0u, 0u}; s.run = Q{0u, 0u, 0u, 0u};\n"
+    << "  Pend pe; for (int i = 0; i < " << 4 << "; ++i) { pe.n[i] = Q{0u, 0u, 0u, 0u}; pe.d[i] = Q{1u, 0u, 0u, 0u}; }\n";
+  for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, pe, cols, params, out, row, LS);\n  __syncthreads();\n";
   o << "}\n";
   return o.str();
 }
