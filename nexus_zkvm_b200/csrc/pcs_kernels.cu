@@ -119,19 +119,33 @@ __global__ void __launch_bounds__(128) quotients_kernel_x4(const QBatchDev* __re
       for (int j = 0; j < 4; ++j) s[r][j] = 0;
     const u32 first = qb->first, count = qb->count;
     const QEntryDev* en = entries + first;
-    for (u32 e = 0; e < count; ++e) {
+    u32 e = 0;
+    for (; e + 4 <= count; e += 4) {   // four columns in flight per thread (the loop is latency bound otherwise), then one reduction
+      uint4 f[4], k[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f[u] = __ldg(reinterpret_cast<const uint4*>(en[e + u].col + row));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) k[u] = __ldg(reinterpret_cast<const uint4*>(en[e + u].c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 fr[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          s[r][0] += (u64)fr[r] * k[u].x; s[r][1] += (u64)fr[r] * k[u].y; s[r][2] += (u64)fr[r] * k[u].z; s[r][3] += (u64)fr[r] * k[u].w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[r][j] = m31_red64(s[r][j]);
+    }
+    for (; e < count; ++e) {           // at most three left: still within 64 bits
       const uint4 f = __ldg(reinterpret_cast<const uint4*>(en[e].col + row));
       const uint4 k = __ldg(reinterpret_cast<const uint4*>(en[e].c));
       const u32 fr[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         s[r][0] += (u64)fr[r] * k.x; s[r][1] += (u64)fr[r] * k.y; s[r][2] += (u64)fr[r] * k.z; s[r][3] += (u64)fr[r] * k.w;
-      }
-      if ((e & 3u) == 3u) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) s[r][j] = m31_red64(s[r][j]);
       }
     }
     const qm31 A = qm31_make(qb->A[0], qb->A[1], qb->A[2], qb->A[3]);
