@@ -523,7 +523,8 @@ static void plan_passes(u32 n, std::vector<PassPlan>& out) {
 template <bool INV, int T, int W, int CB, int NZ>
 static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
   constexpr int threads = 1 << (T - 4);
-  constexpr size_t smem = (size_t)CB << (T + 2);
+  static const size_t pad = getenv("NB200_FFT_PAD_SMEM") ? (size_t)atoi(getenv("NB200_FFT_PAD_SMEM")) * 1024 : 0;   // occupancy experiments
+  const size_t smem = ((size_t)CB << (T + 2)) + pad;
   static bool attr_set = false;
   if (!attr_set) {
     NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_kernel<INV, T, W, CB, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
