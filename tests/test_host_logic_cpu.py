@@ -89,3 +89,53 @@ def test_oracle_and_builder_agree_on_register_counts():
     # both parsers accept the same program and the oracle's interpreter stays inside the declared register file
     m = M.AddMachine(log_size=8, n_lanes=2)
     orc.Prover(m.words)
+
+
+# ---- arithmetic identities the generated kernels rely on (csrc/jit.cu prelude, m31.cuh m31_red64) -----------------------------
+def _red64_model(x):
+    """Bit-level model of m31_red64: y = 2 * hi + lo (mad.wide), s = (yl & P) + funnelshift_r(yl, yh, 31), r = umin(s, s - P)."""
+    P = (1 << 31) - 1
+    M32 = (1 << 32) - 1
+    hi, lo = x >> 32, x & M32
+    y = 2 * hi + lo
+    assert y < 3 << 32
+    yl, yh = y & M32, y >> 32
+    s = (yl & P) + (((yh << 32 | yl) >> 31) & M32)
+    assert s <= P + 5 and s <= M32
+    return min(s, (s - P) & M32)
+
+
+def test_red64_is_the_canonical_residue_of_any_u64():
+    import random
+    P = (1 << 31) - 1
+    rnd = random.Random(7)
+    worst = 4 * (P - 1) * P + P                       # four products of a canonical by a value <= P, plus a canonical carry-in
+    assert worst < 1 << 64
+    cases = [0, 1, P - 1, P, P + 1, 2 * P, (1 << 32) - 1, 1 << 32, (1 << 62), (1 << 63) - 1, (1 << 64) - 1, worst, worst - 1]
+    cases += [rnd.getrandbits(64) for _ in range(20000)]
+    cases += [k * P + d for k in (1, 2, 3, (1 << 33) - 1, (1 << 33)) for d in (-1, 0, 1) if 0 <= k * P + d < 1 << 64]
+    for x in cases:
+        assert _red64_model(x) == x % P, hex(x)
+
+
+def test_qmac_regrouping_equals_qm31_multiplication():
+    """r_j = sum of four products with the derived multipliers (P - y1, P - y3, 2 y2 - y3, y2 + 2 y3, P - (y2 + 2 y3)) is (acc + x * y)_j."""
+    import random
+    from nexus_zkvm_b200 import field as F
+    P = (1 << 31) - 1
+    rnd = random.Random(11)
+    edge = [0, 1, P - 1]
+    for trial in range(3000):
+        pick = (lambda: rnd.choice(edge)) if trial < 300 else (lambda: rnd.randrange(P))
+        x, y, acc = tuple(pick() for _ in range(4)), tuple(pick() for _ in range(4)), tuple(pick() for _ in range(4))
+        ny1, ny3 = P - y[1], P - y[3]
+        gp = (2 * y[3] + y[2]) % P
+        g = (2 * y[2] - y[3]) % P
+        h = P - gp
+        r = (acc[0] + x[0] * y[0] + x[1] * ny1 + x[2] * g + x[3] * h,
+             acc[1] + x[0] * y[1] + x[1] * y[0] + x[2] * gp + x[3] * g,
+             acc[2] + x[0] * y[2] + x[1] * ny3 + x[2] * y[0] + x[3] * ny1,
+             acc[3] + x[0] * y[3] + x[1] * y[2] + x[2] * y[1] + x[3] * y[0])
+        assert all(v < 1 << 64 for v in r)
+        want = F.qm31_add(acc, F.qm31_mul(x, y))
+        assert tuple(_red64_model(v) for v in r) == tuple(want)
