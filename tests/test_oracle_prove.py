@@ -93,3 +93,28 @@ def test_oracle_fold_ops_are_linear_and_grind_is_minimal():
         return 128 if v == 0 else (v & -v).bit_length() - 1
     n = orc.grind(digest, 9)
     assert tz(n) >= 9 and all(tz(k) < 9 for k in range(n))
+
+
+def test_half_domain_decomposition_used_by_the_quotient_step():
+    """in the circle-FFT basis a polynomial with coefficients [lo | hi] (2^(m+1) of them) equals lo on
+    CanonicCoset(m).circle_domain() (the top basis element pi^(m-1)(x) vanishes there) and lo + t * hi on the first half of
+    CanonicCoset(m+1).circle_domain() with ONE constant t.  Checked here with the oracle's evaluate / eval_at_point."""
+    P = (1 << 31) - 1
+    rng = np.random.default_rng(0)
+    for m in (3, 6):
+        c = rng.integers(0, P, size=1 << (m + 1), dtype=np.uint32)
+        lo, hi = c[:1 << m].copy(), c[1 << m:].copy()
+        ev_lo = orc.evaluate(lo, m)                           # bit-reversed evaluations of lo on canonic(m)
+        for i in range(1 << m):
+            x, y = orc.circle_domain_at(m, i)
+            v = orc.eval_at_point(c, (x, 0, 0, 0), (y, 0, 0, 0))
+            assert tuple(int(t) for t in v) == (int(ev_lo[orc.bit_reverse_index(i, m)]), 0, 0, 0)
+        z = np.zeros(1 << m, np.uint32)
+        full = orc.evaluate(c, m + 1)
+        e_lo = orc.evaluate(np.concatenate([lo, z]), m + 1)
+        e_hi = orc.evaluate(np.concatenate([hi, z]), m + 1)
+        h = 1 << m
+        ts = {(int(full[i]) - int(e_lo[i])) % P * orc.m31_inv(int(e_hi[i])) % P for i in range(h) if int(e_hi[i])}
+        assert len(ts) == 1
+        t = ts.pop()
+        assert all((int(e_lo[i]) + t * int(e_hi[i])) % P == int(full[i]) for i in range(h))
