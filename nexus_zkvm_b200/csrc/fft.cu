@@ -158,37 +158,45 @@ __global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_kern
   constexpr int NROUNDS_RUN = FUSE_TOP ? NFULL : NROUNDS;
   if (FUSE_TOP) {
     const u32 t2 = (NZ > 0) ? 0u : __ldg(p.tw2 + (p.tw_len - (1u << (p.tn - (lo + L - 1)))) + tile_hi);
+    // all loads first (see the plain path below), then the top-layer butterflies and the shared stores
+    constexpr int SBF = (CB >= 2) ? 2 : 1;   // two columns (up to 8 x 128 bits) in flight per thread
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
+    for (int cb0 = 0; cb0 < CB; cb0 += SBF) {
+    uint4 va[SBF][2], vb[SBF][2];
+#pragma unroll
+    for (int cc = 0; cc < SBF; ++cc) {
+      const int c = cb0 + cc;
+      const u32* __restrict__ scol = p.src + (size_t)(col0 + (c < (int)ncb ? c : 0)) * p.src_stride;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        size_t g, g2;
+        if (AFFINE) { g = g0 + it * gstep; g2 = g0 + (it + 2) * gstep; }
+        else {
+          const u32 s = (tid + it * NT) * 4, s2 = (tid + (it + 2) * NT) * 4;
+          g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
+          g2 = W ? (gbase | ((size_t)(s2 >> W) << lo) | (s2 & ((1u << W) - 1u))) : (gbase | s2);
+        }
+        va[cc][it] = make_uint4(0, 0, 0, 0); vb[cc][it] = make_uint4(0, 0, 0, 0);
+        if (c < (int)ncb && g < p.src_len) va[cc][it] = __ldg(reinterpret_cast<const uint4*>(scol + g));
+        if (NZ == 0 && c < (int)ncb && g2 < p.src_len) vb[cc][it] = __ldg(reinterpret_cast<const uint4*>(scol + g2));
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < SBF; ++cc) {
+      const int c = cb0 + cc;
       if (c < (int)ncb) {
-        const u32* __restrict__ scol = p.src + (size_t)(col0 + c) * p.src_stride;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-          u32 ph; size_t g;
-          if (AFFINE) { ph = phys0 + it * NT * 4; g = g0 + it * gstep; }
-          else {
-            const u32 s = (tid + it * NT) * 4;
-            ph = swz2(s);
-            g = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
-          }
-          u32 ph2; size_t g2;
-          if (AFFINE) { ph2 = phys0 + (it + 2) * NT * 4; g2 = g0 + (it + 2) * gstep; }
-          else {
-            const u32 s = (tid + (it + 2) * NT) * 4;
-            ph2 = swz2(s);
-            g2 = W ? (gbase | ((size_t)(s >> W) << lo) | (s & ((1u << W) - 1u))) : (gbase | s);
-          }
-          uint4 a = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
-          if (g < p.src_len) a = __ldg(reinterpret_cast<const uint4*>(scol + g));
+          const u32 ph = AFFINE ? (phys0 + it * NT * 4) : swz2((tid + it * NT) * 4);
+          const u32 ph2 = AFFINE ? (phys0 + (it + 2) * NT * 4) : swz2((tid + (it + 2) * NT) * 4);
+          uint4 a = va[cc][it], b4 = vb[cc][it];
           if (NZ > 0) b4 = a;   // the partner is a zero-extension word: v0 + t*0 = v0 - t*0
-          else {
-            if (g2 < p.src_len) b4 = __ldg(reinterpret_cast<const uint4*>(scol + g2));
-            butterfly_dbl(a.x, b4.x, t2); butterfly_dbl(a.y, b4.y, t2); butterfly_dbl(a.z, b4.z, t2); butterfly_dbl(a.w, b4.w, t2);
-          }
+          else { butterfly_dbl(a.x, b4.x, t2); butterfly_dbl(a.y, b4.y, t2); butterfly_dbl(a.z, b4.z, t2); butterfly_dbl(a.w, b4.w, t2); }
           *reinterpret_cast<uint4*>(sm + (c << T) + ph) = a;
           *reinterpret_cast<uint4*>(sm + (c << T) + ph2) = b4;
         }
       }
+    }
     }
   } else {
     // Loads of SB columns (SB * 4 x 128 bits per thread) are all issued before the first shared store: the compiler otherwise emits
