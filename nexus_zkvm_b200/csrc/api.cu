@@ -356,18 +356,22 @@ nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batch
   std::vector<ColRef> cols;
   LeafSink sink;
   const long leaf_batch = leaf_sink_batch(n_cols, log_sizes, n_batches);
-  if (leaf_batch >= 0) NB_TRY(merkle_tree_alloc(ctx, max_log, &sink.tree));
+  // batches allocated here stay in the caller's arrays (the caller owns them either way); the partial tree does not leak
+  auto fail = [&](nb200_status st) { if (sink.tree) { nb200_tree_free(ctx, sink.tree); sink.tree = nullptr; } return st; };
+#define NB_TRYC(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail(_s); } while (0)
+  if (leaf_batch >= 0) NB_TRYC(merkle_tree_alloc(ctx, max_log, &sink.tree));
   for (size_t b = 0; b < n_batches; ++b) {
-    if (!evals_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &evals_io[b]));
-    if (!coeffs_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &coeffs_io[b]));
-    if (!lde_io[b]) NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + log_blowup, &lde_io[b]));
-    NB_ARG(ctx, evals_io[b]->n_cols == n_cols[b] && evals_io[b]->log_size == log_sizes[b] && coeffs_io[b]->n_cols == n_cols[b] &&
-                    coeffs_io[b]->log_size == log_sizes[b] && lde_io[b]->n_cols == n_cols[b] && lde_io[b]->log_size == log_sizes[b] + log_blowup,
-           "commit_host: batch shapes");
-    NB_TRY(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d,
-                                      nullptr, (long)b == leaf_batch ? &sink : nullptr));
+    if (!evals_io[b]) NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &evals_io[b]));
+    if (!coeffs_io[b]) NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &coeffs_io[b]));
+    if (!lde_io[b]) NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + log_blowup, &lde_io[b]));
+    if (!(evals_io[b]->n_cols == n_cols[b] && evals_io[b]->log_size == log_sizes[b] && coeffs_io[b]->n_cols == n_cols[b] &&
+          coeffs_io[b]->log_size == log_sizes[b] && lde_io[b]->n_cols == n_cols[b] && lde_io[b]->log_size == log_sizes[b] + log_blowup))
+      return fail(set_err(ctx, NB200_ERR_ARG, "commit_host: batch shapes"));
+    NB_TRYC(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d,
+                                       nullptr, (long)b == leaf_batch ? &sink : nullptr));
     for (size_t c = 0; c < n_cols[b]; ++c) cols.push_back(ColRef{lde_io[b]->col(c), lde_io[b]->log_size});
   }
+#undef NB_TRYC
   NB_TRY(merkle_commit(ctx, cols, tree_out, sink.tree));
   if (root) memcpy(root, (*tree_out)->root, 32);
   return NB200_OK;

@@ -116,33 +116,43 @@ nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const s
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
   trace_mark(ctx, nullptr);
   SchemeTree t;
+  for (size_t b = 0; b < n; ++b) evals_out[b] = nullptr;
   // leaf hashes are continued chunk by chunk under the PCIe copy when one batch holds all the largest columns
   LeafSink sink;
   const long leaf_batch = leaf_sink_batch(n_cols, log_sizes, n);
-  if (leaf_batch >= 0) NB_TRY(merkle_tree_alloc(ctx, max_log, &sink.tree));
+  // on any failure: nothing is handed to the caller, nothing stays allocated
+  auto fail = [&](nb200_status st) {
+    for (size_t b = 0; b < n; ++b) if (evals_out[b]) { nb200_cols_free(ctx, evals_out[b]); evals_out[b] = nullptr; }
+    if (sink.tree) nb200_tree_free(ctx, sink.tree);
+    free_tree(ctx, t);
+    return st;
+  };
+#define NB_TRYC(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail(_s); } while (0)
+  if (leaf_batch >= 0) NB_TRYC(merkle_tree_alloc(ctx, max_log, &sink.tree));
   for (size_t b = 0; b < n; ++b) {
-    nb200_cols *ev = nullptr, *co = nullptr, *lde = nullptr;
-    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &ev));
-    evals_out[b] = ev;
-    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &co));
+    nb200_cols *co = nullptr, *lde = nullptr, *hx = nullptr;
+    NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &evals_out[b]));
+    NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b], &co));
     t.coeffs.push_back(co);
-    NB_TRY(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + s->log_blowup, &lde));
+    NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], log_sizes[b] + s->log_blowup, &lde));
     t.ldes.push_back(lde);
     // The copy from the host is PCIe-bound and leaves the SMs mostly idle: if the AIR's degree bound is known to need the half-coset
     // evaluations of these polynomials later (component_quotients, Q_HALF), compute them now, chunk by chunk, in that shadow.
-    nb200_cols* hx = nullptr;
     const u32 lde_log = log_sizes[b] + s->log_blowup;
     if (s->hint_log_expand == s->log_blowup + 1 && lde_log > 8) {
-      NB_TRY(twiddles_prepare(ctx, lde_log + 1));
-      NB_TRY(nb200_cols_alloc(ctx, n_cols[b], lde_log, &hx));
+      NB_TRYC(twiddles_prepare(ctx, lde_log + 1));
+      NB_TRYC(nb200_cols_alloc(ctx, n_cols[b], lde_log, &hx));
     }
     t.half_ext.push_back(hx);
-    NB_TRY(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, ev->d, co->d, lde->d, hx ? hx->d : nullptr,
-                                      (long)b == leaf_batch ? &sink : nullptr));
+    NB_TRYC(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, evals_out[b]->d, co->d, lde->d, hx ? hx->d : nullptr,
+                                       (long)b == leaf_batch ? &sink : nullptr));
   }
+#undef NB_TRYC
   trace_mark(ctx, "commit(host): h2d+ifft+lde");
-  nb200_status st = finish_tree(ctx, t, ch, sink.tree);
-  if (st != NB200_OK) { free_tree(ctx, t); return st; }
+  nb200_tree* pre = sink.tree;
+  sink.tree = nullptr;                     // consumed by merkle_commit (also on failure)
+  nb200_status st = finish_tree(ctx, t, ch, pre);
+  if (st != NB200_OK) return fail(st);
   trace_mark(ctx, "commit: merkle");
   if (root) memcpy(root, t.merkle->root, 32);
   s->trees.push_back(std::move(t));
