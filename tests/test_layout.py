@@ -76,32 +76,3 @@ def test_generic_fallback_is_conflict_free(T, W):
     for base in range(0, 1 << T, 32):
         assert wf32([swz(s) for s in range(base, base + 32)]) == 1
 
-
-# ---- groundwork for the 48-warp (8 values per thread, radix-8 rounds) variant of the tile kernel, DESIGN §8 item 1 -----------------
-def swz8(s):
-    """XOR swizzle found by search: bank bit 2 ^= s5 ^ s12, bit 3 ^= s6 ^ s8, bit 4 ^= s7 (keeps aligned 4-word groups intact)."""
-    return s ^ ((((s >> 5) ^ (s >> 12)) & 1) << 2) ^ ((((s >> 6) ^ (s >> 8)) & 1) << 3) ^ (((s >> 7) & 1) << 4)
-
-
-def insert8(tau, b, k):
-    return ((tau >> b) << (b + 3)) | (k << b) | (tau & ((1 << b) - 1))
-
-
-@pytest.mark.parametrize("T,bs", [(12, [0, 3, 6, 9]), (12, [4, 7, 9]), (13, [0, 3, 6, 9, 10]), (13, [4, 7, 10]), (12, [5, 8, 9]), (12, [6, 9])])
-def test_radix8_swizzle_candidate_is_conflict_free(T, bs):
-    """Every shared-memory access pattern a radix-8 (3 layers per round, 2^(T-3) threads) version of the tile kernel would issue:
-    the 128-bit round at bit 0 (two accesses per thread), 32-bit rounds at the listed bit positions, 128-bit staging."""
-    nthreads = 1 << (T - 3)
-    for b in bs:
-        for warp in range(0, nthreads, 32):
-            lanes = range(warp, warp + 32)
-            if b == 0:
-                for q in range(2):
-                    assert wf128([swz8(insert8(t, 0, 4 * q)) for t in lanes]) == 1
-            else:
-                for k in range(8):
-                    assert wf32([swz8(insert8(t, b, k)) for t in lanes]) == 1
-    for base in range(0, 1 << T, 128):
-        assert wf128([swz8(s) for s in range(base, base + 128, 4)]) == 1
-    assert sorted(swz8(s) for s in range(1 << T)) == list(range(1 << T))
-    assert all(swz8(s) // 4 == swz8(s + 3) // 4 and swz8(s + 1) == swz8(s) + 1 for s in range(0, 1 << T, 4))
