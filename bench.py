@@ -327,6 +327,8 @@ def main():
                         # (46.9 GB / (1012 x 2^20) = 44.2 B per trace element: two passes each for iFFT and LDE), scaled to this
                         # step's element count
                         "traffic": 44.2 * elems, "traffic_unit": "B per step (all FFT passes)", "algorithmic": fft_bytes,
+                        # the same kernels seen as DRAM movers: ncu traffic / live event time / peak (BASELINE north star: >= 0.6)
+                        "traffic_frac": 44.2 * elems / ((t_ifft + t_fft) * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": peak_src,
                         "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
                         "time_share": {"fft": (t_ifft + t_fft) / (t_ifft + t_fft + t_mrk), "merkle": t_mrk / (t_ifft + t_fft + t_mrk)}}
