@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — the hot path's headline measurement (BASELINE.json configs[1]):
-2^20-row synthetic trace, LDE (Circle iFFT + FFT, blow-up 2) + Blake2s Merkle commit of the reference's three
-trace trees (27 preprocessed + 347 main + 1012 interaction M31 columns) on B200.
+"""bench.py — the hot path's headline measurement: RISC-V cycles PROVED per second at 2^20 rows (BASELINE.json `metric`).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+One "step" = ONE WHOLE PROOF of the Nexus-shaped synthetic machine (nexus_zkvm_b200/machine.py, 21 ADD lanes: 3 / 339 / 1012
+committed columns + 4 composition columns — the reference's 27 / 347 / 1012) at 2^log_rows rows, i.e. everything
+/root/reference prover/src/machine.rs:186-290 hands to Stwo: three tree commits (Circle iFFT, LDE, Blake2s Merkle), the LogUp
+interaction trace, constraint quotients, the composition commit, OODS evaluation, DEEP quotients, FRI, proof of work, query
+decommitments and the postcard proof bytes.  Host-side trace FILLING is outside the step (the north star keeps it on the CPU).
 
-One "step" = one pass of the commit path over one 2^20-row trace segment per GPU (weak scaling: every rank
-commits its own segment, then the Merkle roots are all-gathered over NCCL).  `value` = rows committed per
-second by the whole job with inputs resident in HBM; `e2e` = the same through the C ABI from pinned HOST
-buffers (H2D of the evaluations and D2H of the roots inside the timed region).
-Inputs (5.4 GiB per segment) are larger than L2, so no explicit L2 flush is needed between iterations.
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference ...                     # CPU arm: the oracle's full prove of the SAME machine, really executed
+    python bench.py --fft-sweep [--gpus N]                   # BASELINE configs[4]: Circle-FFT M31 elems/s, 2^16..2^26
+    python bench.py --log-rows 22 --steps 2 --warmup 1       # BASELINE configs[2]: a 2^22-row full proof on one GPU
+
+  value   cycles/s with the filled trace (trees 0+1 evaluations) already RESIDENT in HBM when the timed region starts;
+  e2e     the same proof through the public host-column API: pinned HOST trace columns in (packed: byte-valued columns travel as
+          u8, the device widens them and applies finalize_columns) -> proof bytes on the host; H2D and D2H inside the timed region;
+  stages / roofline   the commit transforms (iFFT + LDE of every committed column: the dominant kernel group) timed alone with
+          CUDA events on the launching stream, against MEASURED_PEAKS.json's HBM bandwidth at 12 algorithmic bytes per trace element;
+  N > 1   weak scaling: every rank proves its own 2^log_rows-row trace segment; the Merkle roots are all-gathered over NCCL.
+Inputs (1.4 GB of evaluations, 45 GB of intermediates per proof) are far larger than L2: no flush is needed between steps.
 """
 import argparse
 import json
@@ -27,25 +35,26 @@ if ROOT not in sys.path:
 P = (1 << 31) - 1
 METRIC = "RISC-V cycles proved/sec @ 2^20 rows"
 UNIT = "cycles/s"
-TREE_COLS = (27, 347, 1012)  # preprocessed+program, main, interaction (SURVEY.md §8 sizing shorthand)
+CONFIG = dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)   # PcsConfig::default() as restated in DESIGN.md
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
-    ap.add_argument("--cols", default=",".join(map(str, TREE_COLS)))
-    ap.add_argument("--log-blowup", type=int, default=1)
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-cols", type=int, default=128)
+    ap.add_argument("--lanes", type=int, default=21)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-log-rows", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
-    ap.add_argument("--no-full-prove", action="store_true")
-    ap.add_argument("--prove-lanes", type=int, default=21)
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--fft-sweep", action="store_true")
+    ap.add_argument("--sweep-logs", default="16,18,20,22,24,26")
+    ap.add_argument("--sweep-mib", type=int, default=1024, help="MiB of evaluations per sweep point and GPU")
     return ap.parse_args()
 
 
@@ -148,65 +157,56 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def synth_trace_torch(torch, dev, log_rows, tree_cols, seed):
-    """Synthetic fixed-length trace in the shape of the reference's three trees (uniform/byte-valued words)."""
-    g = torch.Generator(device=dev)
-    g.manual_seed(0x5EED0000 + seed)
-    n = 1 << log_rows
-    out = []
-    for t, c in enumerate(tree_cols):
-        hi = 256 if t == 1 else P  # main trace is mostly byte limbs / flags; the rest uniform in [0, P)
-        out.append(torch.randint(0, hi, (c, n), generator=g, device=dev, dtype=torch.int32))
-    return out
+def workload_config(args, m, world):
+    nc = m.air.n_columns()
+    return {"workload": f"full STARK proof (stwo::prover::prove + the 3 trace-tree commits + LogUp interaction trace) of a 2^{args.log_rows}-row synthetic "
+                        f"trace, {nc[0]}+{nc[1]}+{nc[2]} M31 columns, blow-up {1 << CONFIG['log_blowup']}, Blake2s Merkle, per GPU",
+            "log_rows": args.log_rows, "columns": int(sum(nc)), "constraints": int(sum(len(c.constraints) for c in m.air.components)),
+            "pcs_config": CONFIG, "l2": "working set (tens of GB per proof) far larger than L2; no flush needed",
+            "sharding": "one trace segment per GPU (weak scaling) + NCCL all-gather of the Merkle roots" if world > 1 else "single GPU"}
 
 
-def cpu_commit_sample(orc, np, log_rows, log_blowup, sample_cols, seed=1):
-    """The oracle's commit (iFFT + LDE + Merkle) over `sample_cols` columns; returns seconds."""
-    rng = np.random.default_rng(seed)
-    ev = rng.integers(0, P, (sample_cols, 1 << log_rows), dtype=np.uint32)
-    orc.twiddles(log_rows + log_blowup)  # twiddle precompute is not part of the timed path (done once per proof)
-    orc.twiddles(log_rows)
+def make_machine(args, log_rows=None):
+    from nexus_zkvm_b200 import machine as M
+    return M.AddMachine(log_size=log_rows or args.log_rows, n_lanes=args.lanes)
+
+
+def oracle_full_prove(m, cols, mult):
+    """One whole proof by the oracle (CPU restatement of the same pipeline), all host threads; returns (seconds, proof, aux)."""
+    from nexus_zkvm_b200 import machine as M
+    from tests.oracle_backend import OracleBackend
     t0 = time.perf_counter()
-    _, lde = orc.interpolate_evaluate_batch(ev, log_blowup)
-    orc.merkle_commit(list(lde))
-    return time.perf_counter() - t0
+    proof, claimed, aux = M.prove(m, OracleBackend(), cols, mult, config=CONFIG)
+    return time.perf_counter() - t0, proof, aux
 
 
 def run_reference(args):
-    """CPU arm: the oracle port (the real reference cannot be built here: Rust + un-vendored stwo, no cargo)."""
-    import numpy as np
-    from oracle import pyoracle as orc
+    """CPU arm: the reference's own prover cannot be built here (Rust + un-vendored stwo, no cargo: DESIGN.md §2), so this times the
+    oracle port's FULL prove of the same machine on the same trace, really executed (no sampling, no extrapolation), on every host core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tree_cols = [int(x) for x in args.cols.split(",")]
-    total_cols = sum(tree_cols)
-    sample = min(args.cpu_sample_cols, total_cols)
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
-    orc.set_num_threads(os.cpu_count() or 1)
-    cores = orc.num_threads()
-    for _ in range(min(args.warmup, 1)):
-        cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, max(2, sample // 8))
-    ts = [cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample, seed=s) for s in range(max(1, min(args.steps, 3)))]
-    t = sum(ts) / len(ts)
-    t_full = t * total_cols / sample
-    value = (1 << args.log_rows) / t_full
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1),
-            "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (M31)",
-            "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, tree_cols),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle), scaled linearly in columns"},
+    from oracle import pyoracle as orc
+    orc.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
+    m = make_machine(args)
+    cols, mult = m.fill_main_trace(seed=0)
+    t, proof, _aux = oracle_full_prove(m, cols, mult)   # ONE step: a 2^20-row CPU proof takes minutes
+    value = (1 << args.log_rows) / t
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (M31)",
+            "data": "synthetic", "impl": "reference", "config": workload_config(args, m, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"one whole 2^{args.log_rows}-row proof of the same machine ({t:.1f} s, {len(proof)} proof bytes), no extrapolation"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "note": "steps/warmup fixed to 1/0: one CPU proof at this size takes minutes"}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, tree_cols):
-    return {"workload": f"configs[1]: 2^{args.log_rows}-row synthetic trace, LDE (blow-up {1 << args.log_blowup}) + Blake2s Merkle commit of "
-                        f"{len(tree_cols)} trees ({'+'.join(map(str, tree_cols))} M31 columns) per GPU",
-            "log_rows": args.log_rows, "columns": sum(tree_cols), "log_blowup": args.log_blowup,
-            "l2": "inputs (5.4 GiB/segment) larger than L2; no flush needed", "sharding": "one trace segment per GPU + NCCL allgather of Merkle roots"}
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 def main():
@@ -217,6 +217,8 @@ def main():
     import numpy as np
     import torch
     import nexus_zkvm_b200 as nb
+    from nexus_zkvm_b200 import machine as M
+    from nexus_zkvm_b200.prover import CudaBackend
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,35 +231,54 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    tree_cols = [int(x) for x in args.cols.split(",")]
-    total_cols = sum(tree_cols)
-    n_rows = 1 << args.log_rows
-
     stream = torch.cuda.Stream(device=dev)
     ctx = nb.Context(local, stream=stream.cuda_stream)
+    if args.fft_sweep:
+        with torch.cuda.stream(stream):
+            run_fft_sweep(args, ctx, torch, dist, dev, stream, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_rows = 1 << args.log_rows
+    m = make_machine(args)
+    be = CudaBackend(ctx)
+    # ---- the filled trace, in pinned host memory, packed: `pc` as u32, every other main column (byte limbs, flags) as u8
+    pc_block = ctx.host_alloc(1, args.log_rows)
+    byte_block = ctx.host_alloc_bytes((m.n_main_columns() - 1) << args.log_rows).reshape(m.n_main_columns() - 1, n_rows)
+    host_cols, mult = m.fill_main_trace(seed=rank, packed_out=(pc_block, byte_block))
+    h2d = pc_block.nbytes + byte_block.nbytes + mult.nbytes + sum(c.nbytes for c in m.preprocessed_columns())
+
     with torch.cuda.stream(stream):
-        evals_t = synth_trace_torch(torch, dev, args.log_rows, tree_cols, seed=rank)
-        evals = [ctx.wrap_device(t.data_ptr(), t.shape[0], args.log_rows) for t in evals_t]
-        ctx.precompute_twiddles(args.log_rows + args.log_blowup)
-        roots_dev = torch.zeros((len(tree_cols), 32), dtype=torch.uint8, device=dev)
+        ctx.precompute_twiddles(args.log_rows + 3)
+        # resident copies of trees 0 + 1 (finalized order) for the HBM-resident headline
+        up = be.prover(m.words, CONFIG)
+        t0_res = up._batches_from_host(m.preprocessed_columns(), True)
+        wide = np.empty((m.n_main_columns(), n_rows), np.uint32)
+        wide[0] = pc_block[0]
+        wide[1:] = byte_block
+        t1_res = [ctx.upload(wide, coset_order=True), ctx.upload(mult[None, :], coset_order=True)]
+        del wide, up
+        roots_dev = torch.zeros((4, 32), dtype=torch.uint8, device=dev)
         gathered = [torch.zeros_like(roots_dev) for _ in range(world)] if world > 1 else None
+        last = {}
 
-        state = {"coeffs": [None] * len(tree_cols), "ldes": [None] * len(tree_cols), "trees": [None] * len(tree_cols)}
-
-        def step():
-            roots = []
-            for t in range(len(tree_cols)):
-                if state["trees"][t] is not None:
-                    state["trees"][t].free()
-                co, ld, tree = ctx.commit_evals([evals[t]], args.log_blowup,
-                                                coeffs=[state["coeffs"][t]] if state["coeffs"][t] is not None else None,
-                                                ldes=[state["ldes"][t]] if state["ldes"][t] is not None else None)
-                state["coeffs"][t], state["ldes"][t], state["trees"][t] = co[0], ld[0], tree
-                roots.append(tree.root)
-            if world > 1:
-                roots_dev.copy_(torch.frombuffer(bytearray(b"".join(roots)), dtype=torch.uint8).view(len(tree_cols), 32), non_blocking=True)
+        def exchange_roots(aux):
+            if world > 1:   # the caps exchange of the north star: 3 x 32 bytes per rank
+                roots_dev[:3].copy_(torch.frombuffer(bytearray(b"".join(aux["roots"])), dtype=torch.uint8).view(3, 32), non_blocking=True)
                 dist.all_gather(gathered, roots_dev)
-            return roots
+
+        def step_resident():
+            proof, claimed, aux = M.prove(m, be, None, None, config=CONFIG, resident=(t0_res, t1_res))
+            exchange_roots(aux)
+            last.update(proof=proof, claimed=claimed, aux=aux)
+            return proof
+
+        def step_e2e():
+            proof, claimed, aux = M.prove(m, be, host_cols, mult, config=CONFIG)
+            exchange_roots(aux)
+            last.update(proof_e2e=proof)
+            return proof
 
         def barrier():
             if world > 1:
@@ -265,7 +286,7 @@ def main():
             torch.cuda.synchronize()
 
         for _ in range(args.warmup):
-            roots = step()
+            step_resident()
         barrier()
         sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if rank == 0 else None
         if sampler:
@@ -274,193 +295,169 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            roots = step()
+            step_resident()
         e1.record(stream)
         barrier()
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_total = float(ms.item())
+        ms_per_step = float(ms.item()) / args.steps
         launches = (ctx.launches - l0) * world
-        ms_per_step = ms_total / args.steps
         value = world * n_rows / (ms_per_step * 1e-3)
 
-        # ---- per-stage breakdown + roofline (rank 0) : CUDA events on the launching stream
-        stages, roofline = None, None
-        if rank == 0 and not args.no_breakdown:
-            peaks = {}
-            try:
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except Exception:
-                pass
-            hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-            t_ifft = t_fft = t_mrk = 0.0
-            reps = 3
-            for t in range(len(tree_cols)):
-                scratch = torch.empty_like(evals_t[t])
-                sc = ctx.wrap_device(scratch.data_ptr(), tree_cols[t], args.log_rows)
-                for rep in range(reps + 1):
-                    scratch.copy_(evals_t[t])
-                    a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-                    a.record(stream); ctx.interpolate(sc); b.record(stream)
-                    lde = state["ldes"][t]
-                    lib_eval(ctx, sc, args.log_blowup, lde); c.record(stream)
-                    tr = ctx.merkle_commit([lde]); d.record(stream)
-                    torch.cuda.synchronize()
-                    tr.free()
-                    if rep > 0:
-                        t_ifft += a.elapsed_time(b) / reps; t_fft += b.elapsed_time(c) / reps; t_mrk += c.elapsed_time(d) / reps
-                del scratch
-            elems = total_cols * n_rows
-            fft_bytes = 12.0 * elems  # fused LDE commit = read 4 + write 8 per trace element
-            ach = fft_bytes / ((t_ifft + t_fft) * 1e-3) / 1e9
-            stages = {"ifft_ms": t_ifft, "lde_fft_ms": t_fft, "merkle_ms": t_mrk,
-                      "ifft_GBps_8B_per_elem": 8.0 * elems / (t_ifft * 1e-3) / 1e9,
-                      "lde_fft_GBps_12B_per_elem": 12.0 * elems / (t_fft * 1e-3) / 1e9,
-                      "merkle_GBps_read": (4.0 * elems * (1 << args.log_blowup)) / (t_mrk * 1e-3) / 1e9,
-                      "fft_Melems_per_s": (elems * (1 + (1 << args.log_blowup))) / ((t_ifft + t_fft) * 1e-3) / 1e6}
-            roofline = {"bound": "hbm", "kernel": "fft_tile_kernel (Circle iFFT + LDE FFT: the 4 pass launches of a column batch)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak,
-                        # dram__bytes_read+write of the 4 FFT launches of the 1012-column tree in profiles/ncu_fft_r01c.txt
-                        # (46.9 GB / (1012 x 2^20) = 44.2 B per trace element: two passes each for iFFT and LDE), scaled to this
-                        # step's element count
-                        "traffic": 44.2 * elems, "traffic_unit": "B per step (all FFT passes)", "algorithmic": fft_bytes,
-                        # the same kernels seen as DRAM movers: ncu traffic / live event time / peak (BASELINE north star: >= 0.6)
-                        "traffic_frac": 44.2 * elems / ((t_ifft + t_fft) * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": peak_src,
-                        "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
-                        "time_share": {"fft": (t_ifft + t_fft) / (t_ifft + t_fft + t_mrk), "merkle": t_mrk / (t_ifft + t_fft + t_mrk)}}
-
-        # ---- e2e: host buffers -> C ABI -> roots on the host, copies inside the timed region
+        # ---- e2e: pinned host columns -> proof bytes on the host, copies inside the timed region
         e2e = None
         if not args.no_e2e:
-            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in evals_t]
-            for h, t in zip(host, evals_t):
-                h.copy_(t)
-            torch.cuda.synchronize()
-            h2d = sum(h.numel() * 4 for h in host)
-
-            host_np = [h.numpy().view(np.uint32) for h in host]
-
-            def e2e_step():
-                # the public host-column entry point: chunked H2D on a side stream overlapped with the transforms of the
-                # previous chunk, then Merkle; the 32-byte root comes back to the host inside the call (D2H per tree)
-                roots_ = []
-                for t in range(len(tree_cols)):
-                    if state["trees"][t] is not None:
-                        state["trees"][t].free()
-                    _, _, _, tree = ctx.commit_host([host_np[t]], args.log_blowup, evals=[evals[t]],
-                                                    coeffs=[state["coeffs"][t]], ldes=[state["ldes"][t]])
-                    state["trees"][t] = tree
-                    roots_.append(tree.root)
-                assert roots_ == roots, "e2e roots differ from the device-resident run"
-                return roots_
-
-            e2e_step()
+            step_e2e()
             barrier()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record(stream)
             for _ in range(args.e2e_steps):
-                e2e_step()
+                pe = step_e2e()
             f1.record(stream)
             barrier()
+            assert pe == last["proof"], "the proof from host columns differs from the HBM-resident one"
             ems = torch.tensor([f0.elapsed_time(f1)], device=dev)
             if world > 1:
                 dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * n_rows / (float(ems.item()) / args.e2e_steps * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 32 * len(tree_cols) * world, "steps": args.e2e_steps}  # whole job
-            del host
+            e2e = {"value": world * n_rows / (float(ems.item()) / args.e2e_steps * 1e-3), "unit": UNIT, "ms_per_step": float(ems.item()) / args.e2e_steps,
+                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": (len(pe) + 4 * 32) * world, "steps": args.e2e_steps,
+                   "host_format": "packed: 1 u32 column + %d u8 columns (widened on the device)" % (m.n_main_columns() - 1)}
 
-    full_prove = None
-    if rank == 0 and world == 1 and not args.no_full_prove:
-        # free the commit-path state first: the full prove needs ~45 GB of its own
-        for t in state["trees"]:
-            if t is not None:
-                t.free()
-        for lst in (state["coeffs"], state["ldes"], evals):
-            for b in lst:
-                if b is not None:
-                    b.free()
-        del evals_t
-        torch.cuda.empty_cache()
+        # ---- stage breakdown + roofline of the dominant kernel group (rank 0): CUDA events on the launching stream
+        stages, roofline = None, None
+        if rank == 0 and not args.no_breakdown:
+            stages, roofline = commit_breakdown(args, ctx, torch, dev, stream, m)
+
+    verified = None
+    if rank == 0 and not args.no_verify:
         try:
-            with torch.cuda.stream(stream):
-                full_prove = run_full_prove(ctx, args, torch)
+            # the oracle's independent verifier accepts the proof (transcript replayed from the returned roots with the ORACLE's channel)
+            from oracle import pyoracle as orc
+            aux, ch = last["aux"], orc.Channel()
+            for byte in aux["associated_data"]:
+                ch.mix_u64(int(byte))
+            for ls in aux["log_sizes"]:
+                ch.mix_u64(ls)
+            ch.mix_root(aux["roots"][0]); ch.mix_root(aux["roots"][1])
+            ch.draw_felts(2)
+            ch.mix_felts(last["claimed"])
+            ch.mix_root(aux["roots"][2])
+            orc.verify(m.words, np.array(aux["params"], dtype=np.uint32), last["proof"], ch, m.column_log_sizes())
+            verified = True
         except Exception as e:
-            full_prove = {"error": repr(e)}
+            verified = f"failed: {e!r}"
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import pyoracle as orc
             orc.set_num_threads(os.cpu_count() or 1)
-            sample = min(args.cpu_sample_cols, total_cols)
-            tcpu = cpu_commit_sample(orc, np, args.log_rows, args.log_blowup, sample)
-            cpu_baseline = {"value": n_rows / (tcpu * total_cols / sample), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                            "sample": f"{sample} of {total_cols} columns at 2^{args.log_rows} rows (iFFT+LDE+Merkle, {tcpu:.1f} s), scaled linearly in columns"}
+            ms_ = make_machine(args, args.cpu_sample_log_rows)
+            cs, mu = ms_.fill_main_trace(seed=0)
+            tcpu, _p, _a = oracle_full_prove(ms_, cs, mu)
+            cpu_baseline = {"value": (1 << args.cpu_sample_log_rows) / tcpu, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                            "sample": f"one whole proof of the same machine at 2^{args.cpu_sample_log_rows} rows ({tcpu:.1f} s); `--impl reference` runs the 2^{args.log_rows}-row proof"}
         except Exception as e:  # the GPU numbers must still be reported
             cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u32 (M31)", "data": "synthetic", "config": workload_config(args, tree_cols),
+                "dtype": "u32 (M31)", "data": "synthetic", "config": workload_config(args, m, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "stages": stages, "full_prove": full_prove, "roots": [r.hex()[:16] for r in roots]}
+                "stages": stages, "proof_bytes": len(last["proof"]), "verified_by_oracle_verifier": verified,
+                "claimed_sums_cancel": M.verify_claimed_sums(last["claimed"]), "roots": [r.hex()[:16] for r in last["aux"]["roots"]]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_full_prove(ctx, args, torch, reps=2):
-    """Extra (non-headline) leg: the whole proof of the Nexus-shaped synthetic machine (nexus_zkvm_b200/machine.py, 21 ADD
-    lanes = 3/339/1012 columns) at 2^log_rows rows through the C ABI from HOST columns: H2D of the filled trace, 3 tree
-    commits, GPU logup interaction trace, constraint quotients, composition commit, OODS, DEEP quotients, FRI, PoW,
-    decommitments, postcard bytes.  Host-side trace filling (numpy) is outside the timed region, as in the north star.
-    The proof is then checked by the oracle's independent verifier (transcript replayed from the returned roots)."""
-    import numpy as np
-    from nexus_zkvm_b200 import machine as M
-    from nexus_zkvm_b200.prover import CudaBackend
-    m = M.AddMachine(log_size=args.log_rows, n_lanes=args.prove_lanes)
-    # the host fills the trace straight into pinned memory handed out by the library (nb200_host_alloc)
-    cols, mult = m.fill_main_trace(seed=1, out=ctx.host_alloc(m.n_main_columns(), args.log_rows))
-    be = CudaBackend(ctx)
-    times = []
-    for _ in range(reps + 1):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        proof, claimed, aux = M.prove(m, be, cols, mult)
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    t = min(times[1:])
-    out = {"ms": t * 1e3, "cycles_per_s": (1 << args.log_rows) / t, "proof_bytes": len(proof), "columns": m.air.n_columns(),
-           "constraints": sum(len(c.constraints) for c in m.air.components), "timing": "host wall clock around the public API, best of %d" % reps,
-           "claimed_sums_cancel": M.verify_claimed_sums(claimed)}
-    try:
-        from oracle import pyoracle as orc
-        ch = orc.Channel()
-        for b in aux["associated_data"]:
-            ch.mix_u64(int(b))
-        for ls in aux["log_sizes"]:
-            ch.mix_u64(ls)
-        ch.mix_root(aux["roots"][0]); ch.mix_root(aux["roots"][1])
-        ch.draw_felts(2)
-        ch.mix_felts(claimed)
-        ch.mix_root(aux["roots"][2])
-        orc.verify(m.words, np.array(aux["params"], dtype=np.uint32), proof, ch, m.column_log_sizes())
-        out["verified_by_oracle_verifier"] = True
-    except Exception as e:
-        out["verified_by_oracle_verifier"] = f"failed: {e!r}"
-    return out
+def commit_breakdown(args, ctx, torch, dev, stream, m):
+    """iFFT + LDE (nb200_interpolate_evaluate) and Merkle (nb200_merkle_commit) of the proof's three trace trees, each timed alone."""
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    nc = m.air.n_columns()
+    big = [nc[0] - 1, nc[1] - 1, nc[2] - 4]     # the 2^log_rows-row columns of each tree (the table component's columns are 2^8 rows)
+    n_rows = 1 << args.log_rows
+    t_fft = t_mrk = 0.0
+    reps = 3
+    for c in big:
+        ev_t = torch.randint(0, P, (c, n_rows), device=dev, dtype=torch.int32)
+        ev = ctx.wrap_device(ev_t.data_ptr(), c, args.log_rows)
+        co, lde = ctx.interpolate_evaluate(ev, CONFIG["log_blowup"])
+        for rep in range(reps + 1):
+            a, b, d = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record(stream); ctx.interpolate_evaluate(ev, CONFIG["log_blowup"], co, lde); b.record(stream)
+            tr = ctx.merkle_commit([lde]); d.record(stream)
+            torch.cuda.synchronize()
+            tr.free()
+            if rep > 0:
+                t_fft += a.elapsed_time(b) / reps; t_mrk += b.elapsed_time(d) / reps
+        co.free(); lde.free(); del ev_t
+    elems = sum(big) * n_rows
+    fft_bytes = 12.0 * elems  # SURVEY §8(d): fused LDE commit = read 4 + write 8 per trace element
+    ach = fft_bytes / (t_fft * 1e-3) / 1e9
+    stages = {"commit_transforms_ms": t_fft, "merkle_ms": t_mrk, "columns": int(sum(big)),
+              "fft_Melems_per_s": elems * (1 + (1 << CONFIG["log_blowup"])) / (t_fft * 1e-3) / 1e6,
+              "merkle_GBps_read": 4.0 * elems * (1 << CONFIG["log_blowup"]) / (t_mrk * 1e-3) / 1e9}
+    traffic = None
+    try:   # measured once per build with ncu (tools/ncu_traffic.py writes it); never a constant baked into this file
+        tj = json.load(open(os.path.join(ROOT, "profiles", "fft_traffic.json")))
+        traffic = float(tj["dram_bytes_per_trace_element"]) * elems
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "commit transforms: fft_tile_async_kernel<inv> + fft_mid_kernel + fft_tile_async_kernel<fwd> (Circle iFFT + LDE FFT of every committed column)",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "traffic_unit": "B per step (profiles/fft_traffic.json: ncu dram bytes of the three kernels)" if traffic else None,
+                "algorithmic": fft_bytes, "peak_source": peak_src,
+                "algorithmic_bytes": "12 B per trace element (read 4, write 8) for iFFT+LDE; x columns x 2^log_rows",
+                "int_pipe_note": "the butterflies are INT32 work: 4 ALU-pipe instructions each, 30 butterflies per trace element (DESIGN.md §4)"}
+    return stages, roofline
 
 
-def lib_eval(ctx, coeffs, log_blowup, out):
-    """evaluate into an existing batch (no allocation inside the timed breakdown)."""
-    import ctypes as C
+def run_fft_sweep(args, ctx, torch, dist, dev, stream, rank, world):
+    """BASELINE configs[4]: Circle-FFT throughput 2^16..2^26 M31 elements, columns sharded over the ranks (independent transforms)."""
+    out = []
+    for lg in [int(x) for x in args.sweep_logs.split(",")]:
+        n_cols = max(1, (args.sweep_mib << 20) // (4 << lg))
+        ev_t = torch.randint(0, P, (n_cols, 1 << lg), device=dev, dtype=torch.int32)
+        ev = ctx.wrap_device(ev_t.data_ptr(), n_cols, lg)
+        ctx.precompute_twiddles(lg)
+        res = {}
+        for name, fn in (("ifft", lambda: ctx.interpolate(ev)), ("fft", lambda: ctx._chk(nbl().nb200_evaluate(ctx._h, ev._h, 0, ev._h)))):
+            ts = []
+            for _ in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                a.record(stream); fn(); b.record(stream)
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t = torch.tensor([min(ts[1:])], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[name] = float(t.item())
+        elems = world * n_cols * (1 << lg)
+        out.append({"log_size": lg, "columns_per_gpu": n_cols, "ifft_ms": res["ifft"], "fft_ms": res["fft"],
+                    "ifft_Gelems_per_s": elems / (res["ifft"] * 1e-3) / 1e9, "fft_Gelems_per_s": elems / (res["fft"] * 1e-3) / 1e9})
+        del ev_t
+    if rank == 0:
+        peaks = load_peaks()
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        best = max(o["ifft_Gelems_per_s"] for o in out)
+        print(json.dumps({"metric": "Circle-FFT M31 elems/sec", "value": best * 1e9, "unit": "elems/s", "n_gpus": world, "higher_is_better": True,
+                          "scaling": "weak", "data": "synthetic", "dtype": "u32 (M31)",
+                          "config": {"workload": "configs[4]: Circle iFFT / FFT sweep, in place, %d MiB of columns per GPU per point" % args.sweep_mib},
+                          "roofline_elems_per_s_at_8B": world * hbm / 8.0 * 1e9, "sweep": out}), flush=True)
+
+
+def nbl():
     import nexus_zkvm_b200 as nb
-    ctx._chk(nb.lib().nb200_evaluate(ctx._h, coeffs._h, C.c_uint32(log_blowup), out._h))
+    return nb.lib()
 
 
 if __name__ == "__main__":

@@ -84,6 +84,10 @@ nb200_status nb200_interpolate(nb200_ctx*, nb200_cols* cols);
  * CanonicCoset(log+log_blowup).circle_domain() — the LDE inside TreeBuilder::commit, machine.rs:228.
  * `out` must be a batch of the same column count and log_size + log_blowup. */
 nb200_status nb200_evaluate(nb200_ctx*, const nb200_cols* coeffs, uint32_t log_blowup, nb200_cols* out);
+/* interpolate_columns + evaluate_polynomials in one call — TreeBuilder::extend_evals followed by the LDE of TreeBuilder::commit
+ * (machine.rs:209-228) without the Merkle step: evals (read only) -> coeffs (same shape) and lde (log_size + log_blowup).  For
+ * 2^16..2^22 rows this runs the fused three-kernel pipeline (csrc/fft_fused.cu); results equal nb200_interpolate + nb200_evaluate. */
+nb200_status nb200_interpolate_evaluate(nb200_ctx*, const nb200_cols* evals, uint32_t log_blowup, nb200_cols* coeffs, nb200_cols* lde);
 /* PolyOps::eval_at_point for every column of a batch at n_points QM31 circle points:
  * points = n_points x {x[4], y[4]}; out = n_cols x n_points x QM31 (column-major by column). */
 nb200_status nb200_eval_at_points(nb200_ctx*, const nb200_cols* coeffs, const uint32_t* points_xy, size_t n_points, uint32_t* out_qm31);
@@ -128,6 +132,15 @@ void nb200_host_free(void*);
 nb200_status nb200_commit_host(nb200_ctx*, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes,
                                size_t n_batches, int coset_order, uint32_t log_blowup, nb200_cols** evals_io, nb200_cols** coeffs_io,
                                nb200_cols** lde_io, nb200_tree** tree_out, uint8_t root[32]);
+
+/* The same with a PACKED host format: batch b holds words of elem_bytes[b] = 1, 2 or 4 bytes (elem_bytes == NULL: all 4).
+ * The reference's main trace is byte limbs, flags and 16-bit halves (prover/src/column.rs:22-604) stored as u32 BaseField
+ * words; shipping them at their natural width cuts the PCIe payload of a 2^20-row proof from 1.4 GB to 0.36 GB.  The device
+ * widens them (and applies finalize_columns when coset_order != 0); values must be canonical (< 2^31 - 1), which every
+ * 1- or 2-byte word is. */
+nb200_status nb200_commit_host_packed(nb200_ctx*, const void* const* host_batches, const uint32_t* elem_bytes, const size_t* n_cols,
+                                      const uint32_t* log_sizes, size_t n_batches, int coset_order, uint32_t log_blowup,
+                                      nb200_cols** evals_io, nb200_cols** coeffs_io, nb200_cols** lde_io, nb200_tree** tree_out, uint8_t root[32]);
 
 /* ---- Blake2sChannel (stwo core/channel/blake2s.rs; used at machine.rs:197-206,240,262) --------------- */
 /* The Fiat-Shamir transcript is sequential host work; it is part of the library so that the Rust shim and the
@@ -179,6 +192,10 @@ nb200_status nb200_scheme_commit(nb200_scheme*, const nb200_cols* const* eval_ba
  * evaluation batches (owned by the caller; nb200_gen_interaction_trace reads them) */
 nb200_status nb200_scheme_commit_host(nb200_scheme*, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes,
                                       size_t n_batches, int coset_order, nb200_channel*, uint8_t root[32], nb200_cols** evals_out);
+/* packed host format (see nb200_commit_host_packed) */
+nb200_status nb200_scheme_commit_host_packed(nb200_scheme*, const void* const* host_batches, const uint32_t* elem_bytes, const size_t* n_cols,
+                                             const uint32_t* log_sizes, size_t n_batches, int coset_order, nb200_channel*, uint8_t root[32],
+                                             nb200_cols** evals_out);
 /* generate_interaction_trace for one component (machine.rs:242-260; LogupTraceGenerator semantics) from the committed
  * preprocessed (tree0) and main (tree1) evaluation batches; params = n_params QM31 (lookup elements).
  * Out: a new batch of 4 * n_logup_columns columns and the component's claimed sum.  SURVEY §8 row f2. */

@@ -150,6 +150,13 @@ class Context:
         self._chk(lib().nb200_evaluate(self._h, coeffs._h, C.c_uint32(log_blowup), out._h))
         return out
 
+    def interpolate_evaluate(self, evals, log_blowup, coeffs=None, lde=None):
+        """evals -> (coeffs, lde) without touching evals (nb200_interpolate_evaluate)."""
+        coeffs = coeffs or self.alloc(evals.n_cols, evals.log_size)
+        lde = lde or self.alloc(evals.n_cols, evals.log_size + log_blowup)
+        self._chk(lib().nb200_interpolate_evaluate(self._h, evals._h, C.c_uint32(log_blowup), coeffs._h, lde._h))
+        return coeffs, lde
+
     def eval_at_points(self, coeffs, points):
         """points: (n_points, 2, 4) uint32 = (x, y) QM31 pairs.  Returns (n_cols, n_points, 4)."""
         pts = np.ascontiguousarray(points, dtype=np.uint32).reshape(-1, 8)
@@ -177,6 +184,35 @@ class Context:
         arr = np.ctypeslib.as_array(buf)[:n].reshape(n_cols, 1 << log_size)
         self._pinned.append((p, buf))
         return arr
+
+    def host_alloc_bytes(self, n_bytes):
+        """Pinned host memory as a flat uint8 array (the packed host formats of nb200_commit_host_packed)."""
+        p = C.c_void_p()
+        if lib().nb200_host_alloc(C.c_size_t(n_bytes), C.byref(p)) != 0:
+            raise Nb200Error("nb200_host_alloc failed")
+        buf = (C.c_uint8 * n_bytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        self._pinned.append((p, arr))
+        return arr
+
+    def commit_host_packed(self, host_batches, log_sizes, log_blowup, coset_order=False):
+        """nb200_commit_host_packed: host_batches are 2-D uint8 / uint16 / uint32 arrays (n_cols x 2^log_size)."""
+        n = len(host_batches)
+        hb = [np.ascontiguousarray(h) if not h.flags["C_CONTIGUOUS"] else h for h in host_batches]
+        ptrs = (C.c_void_p * n)(*[h.ctypes.data for h in hb])
+        eb = (C.c_uint32 * n)(*[h.dtype.itemsize for h in hb])
+        ncols = (C.c_size_t * n)(*[h.shape[0] for h in hb])
+        logs = (C.c_uint32 * n)(*[int(x) for x in log_sizes])
+        ev, co, ld = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+        tree = C.c_void_p()
+        root = (C.c_uint8 * 32)()
+        self._chk(lib().nb200_commit_host_packed(self._h, ptrs, eb, ncols, logs, C.c_size_t(n), C.c_int(1 if coset_order else 0), C.c_uint32(log_blowup),
+                                                 ev, co, ld, C.byref(tree), root))
+        self.sync()
+        evals = [Columns(self, C.c_void_p(ev[i])) for i in range(n)]
+        coeffs = [Columns(self, C.c_void_p(co[i])) for i in range(n)]
+        ldes = [Columns(self, C.c_void_p(ld[i])) for i in range(n)]
+        return evals, coeffs, ldes, MerkleTree(self, tree, bytes(root), ldes)
 
     def commit_host(self, host_batches, log_blowup, coset_order=False, evals=None, coeffs=None, ldes=None):
         """Commit from HOST batches (2-D uint32 arrays; pinned for copy/compute overlap): returns (evals, coeffs, ldes, tree)."""

@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
 # ---- cubin cache for the run-time specialised AIR kernels (csrc/jit.cu) ---------------------------------------------
 JIT_CACHE = os.path.join(HERE, "jit_cache")
 # (log_size, n_lanes, logup_in_pairs): bench.py / tools/prove_trace.py, __graft_entry__.smoke and the machines of tests/test_gpu_*.py
-SHIPPED_MACHINES = [(20, 21, False), (8, 1, False), (8, 2, False), (8, 2, True), (8, 3, False), (9, 1, False), (9, 2, False),
+SHIPPED_MACHINES = [(20, 21, False), (16, 21, False), (8, 1, False), (8, 2, False), (8, 2, True), (8, 3, False), (9, 1, False), (9, 2, False),
                     (9, 2, True), (10, 1, False), (12, 3, False)]
 
 

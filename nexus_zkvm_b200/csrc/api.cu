@@ -61,6 +61,7 @@ void nb200_ctx_destroy(nb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   fft_drop_tables(ctx);
+  fft_fused_release(ctx);
   if (ctx->tw.d_tw) cudaFree(ctx->tw.d_tw);
   if (ctx->tw.d_itw) cudaFree(ctx->tw.d_itw);
   if (ctx->tw.d_tw2) cudaFree(ctx->tw.d_tw2);
@@ -92,7 +93,8 @@ nb200_status nb200_sync(nb200_ctx* ctx) {
 
 nb200_status nb200_set_flavor(nb200_ctx* ctx, int merkle_hash, int draw_domain_sep, int pow_variant) {
   if (!ctx) return NB200_ERR_ARG;
-  NB_ARG(ctx, (merkle_hash == 0 || merkle_hash == 1) && (draw_domain_sep == 0 || draw_domain_sep == 1) && (pow_variant == 0 || pow_variant == 1), "bad flavor");
+  NB_ARG(ctx, (merkle_hash == 0 || merkle_hash == 1) && (draw_domain_sep == 0 || draw_domain_sep == 1), "bad flavor");
+  NB_ARG(ctx, pow_variant == 0, "pow_variant: only 0 (trailing zero bits of Blake2s(digest || nonce)) is implemented");
   ctx->merkle_hash = merkle_hash; ctx->draw_domain_sep = draw_domain_sep; ctx->pow_variant = pow_variant;
   return NB200_OK;
 }
@@ -290,9 +292,11 @@ long leaf_sink_batch(const size_t* n_cols, const u32* log_sizes, size_t n_batche
   return count == 1 ? idx : -1;
 }
 
-nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext, LeafSink* leaf) {
+nb200_status upload_transform_pipelined(nb200_ctx* ctx, const void* host_v, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext, LeafSink* leaf, u32 elem_bytes) {
   if (n_cols == 0) return NB200_OK;
+  const uint8_t* host = (const uint8_t*)host_v;
+  const bool staged = coset_order || elem_bytes != 4;   // the chunk lands in a staging buffer and a kernel writes d_evals
   if (!ctx->copy_stream) {
     NB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -307,33 +311,36 @@ nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t 
   if (leaf && leaf->tree) chunk = (chunk + 15) & ~(size_t)15;   // whole 16-column Blake2s message blocks per chunk
   if (chunk > n_cols) chunk = n_cols;
   u32* tmp[2] = {nullptr, nullptr};
-  if (coset_order) for (int i = 0; i < 2; ++i) NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp[i], chunk * len * 4));
+  if (staged) for (int i = 0; i < 2; ++i) {
+    cudaError_t e = dmalloc(ctx, (void**)&tmp[i], chunk * len * elem_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); dfree(ctx, tmp[0]); return set_err(ctx, NB200_ERR_OOM, "pipelined upload: staging buffers"); }
+  }
+  auto done = [&](nb200_status st) { if (staged) { dfree(ctx, tmp[0]); dfree(ctx, tmp[1]); } return st; };
+#define NB_CUDAP(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return done(set_err(ctx, NB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e))); } while (0)
   // the copy stream must not overtake work already queued on the compute stream that still reads the targets
-  NB_CUDA(ctx, cudaEventRecord(ctx->done_ev[0], ctx->stream));
-  NB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[0], 0));
+  NB_CUDAP(cudaEventRecord(ctx->done_ev[0], ctx->stream));
+  NB_CUDAP(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[0], 0));
   nb200_status st = NB200_OK;
   size_t k = 0;
   for (size_t c0 = 0; c0 < n_cols && st == NB200_OK; c0 += chunk, ++k) {
     const size_t nc = std::min(chunk, n_cols - c0);
     const int slot = (int)(k & 1);
-    u32* dst = coset_order ? tmp[slot] : d_evals + c0 * len;
-    if (coset_order && k >= 2) NB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot], 0));  // tmp[slot] consumed?
-    NB_CUDA(ctx, cudaMemcpyAsync(dst, host + c0 * len, nc * len * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    NB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
-    NB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
-    if (coset_order) {
-      st = reorder_coset_to_bitrev(ctx, tmp[slot], d_evals + c0 * len, nc, log_size);
-      if (st == NB200_OK) NB_CUDA(ctx, cudaEventRecord(ctx->done_ev[slot], ctx->stream));
+    void* dst = staged ? (void*)tmp[slot] : (void*)(d_evals + c0 * len);
+    if (staged && k >= 2) NB_CUDAP(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot], 0));  // tmp[slot] consumed?
+    NB_CUDAP(cudaMemcpyAsync(dst, host + c0 * len * elem_bytes, nc * len * elem_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NB_CUDAP(cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
+    NB_CUDAP(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
+    if (staged) {
+      st = expand_reorder(ctx, tmp[slot], elem_bytes, d_evals + c0 * len, nc, log_size, coset_order);
+      if (st == NB200_OK) NB_CUDAP(cudaEventRecord(ctx->done_ev[slot], ctx->stream));
     }
-    if (st == NB200_OK) st = fft_interpolate(ctx, d_evals + c0 * len, d_coeffs + c0 * len, nc, log_size);
-    if (st == NB200_OK) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_lde + c0 * lde_len, log_size + log_blowup, nc);
-    // optional: the same polynomials on the first half of the next larger canonic domain (half-domain transform, fft.cu)
-    if (st == NB200_OK && d_half_ext) st = fft_evaluate(ctx, d_coeffs + c0 * len, log_size, d_half_ext + c0 * lde_len, log_size + log_blowup, nc, log_size + log_blowup + 1);
+    // iFFT + LDE (+ optionally the same polynomials on the first half of the next larger canonic domain) of this chunk
+    if (st == NB200_OK) st = commit_transforms(ctx, d_evals + c0 * len, d_coeffs + c0 * len, d_lde + c0 * lde_len, d_half_ext ? d_half_ext + c0 * lde_len : nullptr, nc, log_size, log_blowup);
     // optional: continue the Merkle leaf hashes over this chunk's LDE columns
     if (st == NB200_OK && leaf && leaf->tree) st = merkle_leaf_absorb(ctx, leaf->tree, d_lde + c0 * lde_len, lde_len, nc, c0, n_cols, c0 + nc == n_cols);
   }
-  if (coset_order) { dfree(ctx, tmp[0]); dfree(ctx, tmp[1]); }
-  return st;
+#undef NB_CUDAP
+  return done(st);
 }
 }  // namespace nb
 
@@ -349,7 +356,14 @@ void nb200_host_free(void* p) { if (p) cudaFreeHost(p); }
 nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes, size_t n_batches,
                                int coset_order, uint32_t log_blowup, nb200_cols** evals_io, nb200_cols** coeffs_io, nb200_cols** lde_io,
                                nb200_tree** tree_out, uint8_t root[32]) {
+  return nb200_commit_host_packed(ctx, (const void* const*)host_batches, nullptr, n_cols, log_sizes, n_batches, coset_order, log_blowup, evals_io, coeffs_io, lde_io, tree_out, root);
+}
+
+nb200_status nb200_commit_host_packed(nb200_ctx* ctx, const void* const* host_batches, const uint32_t* elem_bytes, const size_t* n_cols, const uint32_t* log_sizes,
+                                      size_t n_batches, int coset_order, uint32_t log_blowup, nb200_cols** evals_io, nb200_cols** coeffs_io, nb200_cols** lde_io,
+                                      nb200_tree** tree_out, uint8_t root[32]) {
   if (!ctx || !host_batches || !evals_io || !coeffs_io || !lde_io || !tree_out) return NB200_ERR_ARG;
+  for (size_t b = 0; elem_bytes && b < n_batches; ++b) NB_ARG(ctx, elem_bytes[b] == 1 || elem_bytes[b] == 2 || elem_bytes[b] == 4, "commit_host: 1, 2 or 4 bytes per host word");
   u32 max_log = 0;
   for (size_t b = 0; b < n_batches; ++b) max_log = std::max(max_log, log_sizes[b] + log_blowup);
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
@@ -368,13 +382,22 @@ nb200_status nb200_commit_host(nb200_ctx* ctx, const uint32_t* const* host_batch
           coeffs_io[b]->log_size == log_sizes[b] && lde_io[b]->n_cols == n_cols[b] && lde_io[b]->log_size == log_sizes[b] + log_blowup))
       return fail(set_err(ctx, NB200_ERR_ARG, "commit_host: batch shapes"));
     NB_TRYC(upload_transform_pipelined(ctx, host_batches[b], n_cols[b], log_sizes[b], coset_order, log_blowup, evals_io[b]->d, coeffs_io[b]->d, lde_io[b]->d,
-                                       nullptr, (long)b == leaf_batch ? &sink : nullptr));
+                                       nullptr, (long)b == leaf_batch ? &sink : nullptr, elem_bytes ? elem_bytes[b] : 4u));
     for (size_t c = 0; c < n_cols[b]; ++c) cols.push_back(ColRef{lde_io[b]->col(c), lde_io[b]->log_size});
   }
 #undef NB_TRYC
   NB_TRY(merkle_commit(ctx, cols, tree_out, sink.tree));
   if (root) memcpy(root, (*tree_out)->root, 32);
   return NB200_OK;
+}
+
+// PolyOps::interpolate_columns + evaluate_polynomials as one call (the transform half of nb200_commit_evals; evaluations are only read)
+nb200_status nb200_interpolate_evaluate(nb200_ctx* ctx, const nb200_cols* evals, uint32_t log_blowup, nb200_cols* coeffs, nb200_cols* lde) {
+  if (!ctx || !evals || !coeffs || !lde) return NB200_ERR_ARG;
+  NB_ARG(ctx, coeffs->n_cols == evals->n_cols && coeffs->log_size == evals->log_size, "interpolate_evaluate: coefficient batch shape");
+  NB_ARG(ctx, lde->n_cols == evals->n_cols && lde->log_size == evals->log_size + log_blowup, "interpolate_evaluate: LDE batch shape");
+  if (lde->log_size >= 1) NB_TRY(twiddles_prepare(ctx, lde->log_size));
+  return commit_transforms(ctx, evals->d, coeffs->d, lde->d, nullptr, evals->n_cols, evals->log_size, log_blowup);
 }
 
 // ---- fused commitment ----
@@ -392,8 +415,7 @@ nb200_status nb200_commit_evals(nb200_ctx* ctx, const nb200_cols* const* eval_ba
     nb200_cols *co = coeffs_io[b], *lde = lde_io[b];
     NB_ARG(ctx, co->n_cols == ev->n_cols && co->log_size == ev->log_size, "commit_evals: coefficient batch shape");
     NB_ARG(ctx, lde->n_cols == ev->n_cols && lde->log_size == ev->log_size + log_blowup, "commit_evals: LDE batch shape");
-    NB_TRY(fft_interpolate(ctx, ev->d, co->d, ev->n_cols, ev->log_size));
-    NB_TRY(fft_evaluate(ctx, co->d, co->log_size, lde->d, lde->log_size, ev->n_cols));
+    NB_TRY(commit_transforms(ctx, ev->d, co->d, lde->d, nullptr, ev->n_cols, ev->log_size, log_blowup));
     for (size_t c = 0; c < lde->n_cols; ++c) cols.push_back(ColRef{lde->col(c), lde->log_size});
   }
   NB_TRY(merkle_commit(ctx, cols, tree_out));

@@ -36,7 +36,13 @@ struct nb200_ctx {
   // scratch for small device->host transfers
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
+  void* fft_tables = nullptr;          // per-ctx circle-twiddle tables (fft.cu)
+  // column-chunk pipeline of the commit transforms (fft_fused.cu): side streams + events, created on first use
+  cudaStream_t chunk_stream[2] = {nullptr, nullptr};
+  cudaEvent_t chunk_ev[3] = {nullptr, nullptr, nullptr};
+  void* comm = nullptr;                // NCCL communicator state (comm.cu), nullptr = single GPU
 };
+#define NB_MAX_DEVICES 64
 
 struct nb200_cols {
   nb200_ctx* ctx = nullptr;
@@ -108,12 +114,17 @@ nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log);
 nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size, u32 tw_log = 0);
 // Circle FFT: coefficients (src, log src_log) zero-extended to dst (log dst_log); src may equal dst if logs match
 nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols, u32 tw_log = 0);
+// evaluations -> coefficients + LDE (+ optionally the half-coset extension the quotient step needs) for one batch (fft_fused.cu)
+nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 log_size, u32 log_blowup);
+void fft_fused_release(nb200_ctx* ctx);
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
+nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32* dst, size_t n_cols, u32 log_size, int coset_order);
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)
 // overlaps the transforms of chunk k.  `host` is n_cols x 2^log_size words (pinned memory for real overlap).
 struct LeafSink { nb200_tree* tree = nullptr; };  // set for the one batch that holds all the largest columns of a tree (incremental leaf hashing)
-nb200_status upload_transform_pipelined(nb200_ctx* ctx, const u32* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
-                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext = nullptr, LeafSink* leaf = nullptr);
+// elem_bytes: width of a host word (4 = u32; 1 / 2 = the packed formats for byte- / halfword-valued columns, expanded on the device)
+nb200_status upload_transform_pipelined(nb200_ctx* ctx, const void* host, size_t n_cols, u32 log_size, int coset_order, u32 log_blowup,
+                                        u32* d_evals, u32* d_coeffs, u32* d_lde, u32* d_half_ext = nullptr, LeafSink* leaf = nullptr, u32 elem_bytes = 4);
 
 struct ColRef { const u32* d; u32 log_size; };
 nb200_status merkle_commit(nb200_ctx* ctx, const std::vector<ColRef>& cols, nb200_tree** out, nb200_tree* pre_leaf = nullptr);

@@ -17,113 +17,12 @@
 //   Shared memory is XOR-swizzled; tests/test_layout.py proves every access pattern conflict-free.
 //   `fft_tile_kernel<INV,T,W>` is the compile-time specialised fast path; `fft_pass_kernel` is the generic
 //   fallback for shapes outside the specialised set.
-#include "common.cuh"
+#include "fft_common.cuh"
 #include "circle_host.h"
 #include <map>
+#include <mutex>
 
 namespace nb {
-
-struct FftPass {
-  const u32* src;     // source columns (column c at src + c*src_stride); zero-extended beyond src_len
-  u32* dst;           // destination columns
-  size_t src_stride, dst_stride;
-  size_t src_len;     // valid words per source column
-  const u32* tw;      // twiddle (or inverse twiddle) bank
-  const u32* tw2;     // the same bank doubled (2t), for m31_mul_dbl
-  const u32* ctw2;    // DOUBLED circle (layer 0) twiddles of this transform size, 2^(n-1) words
-  u32 tw_len;         // bank length (2^k)
-  u32 n_cols;
-  u32 n;              // log size of the transform
-  u32 lo;             // first layer of this pass
-  u32 T, W;           // tile log, width log (L = T - W layers)
-  u32 cb;             // columns per CTA
-  u32 scale;          // multiply outputs by this (interpolate last pass) if apply_scale
-  u32 apply_scale;
-  u32 tn;             // log size of the canonic domain whose twiddle arrays are used (= n, or n + 1 for the half-domain transforms)
-  u32 ztop;           // forward transforms of zero-extended input: layers >= ztop are copies (= log2 of the source length)
-};
-
-__device__ __forceinline__ void butterfly(u32& v0, u32& v1, u32 t) {
-  u32 tmp = m31_mul(v1, t);
-  v1 = m31_sub(v0, tmp);
-  v0 = m31_add(v0, tmp);
-}
-__device__ __forceinline__ void ibutterfly(u32& v0, u32& v1, u32 it) {
-  u32 tmp = v0;
-  v0 = m31_add(tmp, v1);
-  v1 = m31_mul(m31_sub(tmp, v1), it);
-}
-
-// twiddle of layer i (>= 1) at index h for a transform of log size n
-__device__ __forceinline__ u32 line_tw(const u32* __restrict__ tw, u32 tw_len, u32 n, u32 i, u32 h) {
-  return __ldg(tw + (tw_len - (1u << (n - i)) + h));
-}
-// circle twiddle (layer 0) at index h: from the first line layer, [x, y] -> [y, -y, -x, x]
-__device__ __forceinline__ u32 circle_tw(const u32* __restrict__ tw, u32 tw_len, u32 n, u32 h) {
-  const u32* l1 = tw + (tw_len - (1u << (n - 1)));
-  u32 q = h >> 2, r = h & 3u;
-  u32 x = __ldg(l1 + 2 * q), y = __ldg(l1 + 2 * q + 1);
-  u32 v = (r < 2) ? y : x;
-  return (r == 1 || r == 2) ? (P31 - v) : v;
-}
-__global__ void circle_table_kernel(const u32* __restrict__ tw, u32 tw_len, u32 n, u32* __restrict__ out) {
-  u32 h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < (1u << (n - 1))) out[h] = circle_tw(tw, tw_len, n, h) << 1;  // doubled, see m31_mul_dbl
-}
-
-// =====================================================================================================
-// fast path: compile-time tile shape
-// =====================================================================================================
-// swizzle keeps aligned groups of 4 words intact (128-bit accesses) and is conflict-free for: 128-bit staging,
-// the 128-bit round at bit 0, and the 32-bit rounds at every bit position used by the schedules below.
-__device__ __forceinline__ u32 swz2(u32 s) { return s ^ (((s >> 5) & 3u) << 2) ^ (((s >> 8) & 1u) << 4); }
-
-// a * t mod P with the twiddle pre-doubled (t2 = 2t < 2^32): the 64-bit product a * t2 has (a*t) >> 31 in its high
-// word and 2 * ((a*t) mod 2^31) in its low word, so the Mersenne fold is one shifted add (LEA.HI) and one min — the
-// mask and the funnel shift of the plain form disappear, which matters because the ALU pipe is the binding one.
-__device__ __forceinline__ u32 m31_mul_dbl(u32 a, u32 t2) {
-  u64 p = (u64)a * t2;
-  u32 s = ((u32)p >> 1) + (u32)(p >> 32);
-  return umin32(s, s - P31);
-}
-__device__ __forceinline__ void butterfly_dbl(u32& v0, u32& v1, u32 t2) {
-  u32 tmp = m31_mul_dbl(v1, t2);
-  v1 = m31_sub(v0, tmp);
-  v0 = m31_add(v0, tmp);
-}
-__device__ __forceinline__ void ibutterfly_dbl(u32& v0, u32& v1, u32 it2) {
-  u32 tmp = v0;
-  v0 = m31_add(tmp, v1);
-  v1 = m31_mul_dbl(m31_sub(tmp, v1), it2);
-}
-
-template <bool INV>
-__device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const int jlo, const u32 triv = 0u) {
-  // tw holds DOUBLED twiddles.  triv bit j (forward only): layer j of this round sits at or above the zero-extension
-  // boundary, its odd inputs are known zeros, so the butterfly degenerates to a copy (no arithmetic).
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j = INV ? jj : 3 - jj;
-    if (j >= jlo) {
-      if (!INV && ((triv >> j) & 1u)) {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
-          v[k0 | (1 << j)] = v[k0];
-        }
-      } else {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int k0 = ((m >> j) << (j + 1)) | (m & ((1 << j) - 1));
-          const int k1 = k0 | (1 << j);
-          const int off = (j == 0 ? 0 : j == 1 ? 8 : j == 2 ? 12 : 14) + (m >> j);
-          if (INV) ibutterfly_dbl(v[k0], v[k1], tw[off]);
-          else butterfly_dbl(v[k0], v[k1], tw[off]);
-        }
-      }
-    }
-  }
-}
 
 // NZ: (forward, top pass of a zero-extended input) the top NZ layers of the pass have all-zero odd inputs -> copies
 template <bool INV, int T, int W, int CB, int NZ>
@@ -463,50 +362,64 @@ __global__ void fft_small_kernel(const FftSmall p) {
 }
 
 // out[i] = in[src(i)]: coset order -> circle-domain order -> bit-reversed  (finalize_columns,
-// /root/reference prover/src/trace/utils.rs:94-106 + utils_external.rs:24-39)
-__global__ void reorder_kernel(const u32* __restrict__ src, u32* __restrict__ dst, u32 log_size, size_t total) {
+// /root/reference prover/src/trace/utils.rs:94-106 + utils_external.rs:24-39); src words are EB bytes wide (packed host format)
+template <int EB>
+__global__ void reorder_kernel(const void* __restrict__ src, u32* __restrict__ dst, u32 log_size, size_t total, int coset_order) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   size_t n = (size_t)1 << log_size;
   size_t c = e >> log_size;
   u32 i = (u32)(e & (n - 1));
-  u32 j = log_size ? (__brev(i) >> (32 - log_size)) : 0;
-  size_t half = n >> 1;
-  size_t s = j < half ? ((size_t)j << 1) : (n - 1 - (((size_t)j - half) << 1));
-  dst[e] = src[c * n + s];
+  size_t s = i;
+  if (coset_order) {
+    u32 j = log_size ? (__brev(i) >> (32 - log_size)) : 0;
+    size_t half = n >> 1;
+    s = j < half ? ((size_t)j << 1) : (n - 1 - (((size_t)j - half) << 1));
+  }
+  u32 v;
+  if (EB == 1) v = reinterpret_cast<const uint8_t*>(src)[c * n + s];
+  else if (EB == 2) v = reinterpret_cast<const uint16_t*>(src)[c * n + s];
+  else v = reinterpret_cast<const u32*>(src)[c * n + s];
+  dst[e] = v;
 }
 
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size) {
-  NB_ARG(ctx, src != dst, "reorder must be out of place");
+  return expand_reorder(ctx, src, 4, dst, n_cols, log_size, 1);
+}
+
+// packed host words (elem_bytes = 1, 2 or 4) -> u32 columns, optionally applying finalize_columns' permutation
+nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32* dst, size_t n_cols, u32 log_size, int coset_order) {
+  NB_ARG(ctx, (const void*)src != (const void*)dst, "reorder must be out of place");
+  NB_ARG(ctx, elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4, "packed columns: 1, 2 or 4 bytes per word");
   size_t total = n_cols << log_size;
   if (total == 0) return NB200_OK;
   u32 threads = 256;
   size_t blocks = (total + threads - 1) / threads;
-  reorder_kernel<<<(u32)blocks, threads, 0, ctx->stream>>>(src, dst, log_size, total);
+  if (elem_bytes == 1) reorder_kernel<1><<<(u32)blocks, threads, 0, ctx->stream>>>(src, dst, log_size, total, coset_order);
+  else if (elem_bytes == 2) reorder_kernel<2><<<(u32)blocks, threads, 0, ctx->stream>>>(src, dst, log_size, total, coset_order);
+  else reorder_kernel<4><<<(u32)blocks, threads, 0, ctx->stream>>>(src, dst, log_size, total, coset_order);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
 
-// ---- circle-twiddle tables (layer 0 of each transform size), cached per ctx ----
-struct CircleTables { std::map<u32, std::pair<u32*, u32*>> by_log; u32 bank_log = 0; };
-static std::map<nb200_ctx*, CircleTables>& circle_cache() { static std::map<nb200_ctx*, CircleTables> m; return m; }
+// ---- circle-twiddle tables (layer 0 of each transform size), owned by the ctx (freed in nb200_ctx_destroy) ----
+struct CircleTables { std::map<u32, std::pair<u32*, u32*>> by_log; };
 void fft_drop_tables(nb200_ctx* ctx) {
-  auto it = circle_cache().find(ctx);
-  if (it == circle_cache().end()) return;
-  for (auto& kv : it->second.by_log) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
-  circle_cache().erase(it);
+  CircleTables* ct = (CircleTables*)ctx->fft_tables;
+  if (!ct) return;
+  for (auto& kv : ct->by_log) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  delete ct;
+  ctx->fft_tables = nullptr;
 }
-static nb200_status circle_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv) {
-  CircleTables& ct = circle_cache()[ctx];
-  if (ct.bank_log != ctx->tw.half_log) {  // the bank was rebuilt: tables stay valid (they hold values, not pointers)
-    ct.bank_log = ctx->tw.half_log;
-  }
+nb200_status fft_circle_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv) {
+  if (!ctx->fft_tables) ctx->fft_tables = new CircleTables();
+  CircleTables& ct = *(CircleTables*)ctx->fft_tables;   // tables hold values derived from the generator, not pointers into the bank
   auto it = ct.by_log.find(n);
   if (it == ct.by_log.end()) {
     u32 *f = nullptr, *g = nullptr;
     size_t len = (size_t)1 << (n - 1);
     NB_CUDA(ctx, cudaMalloc(&f, len * 4));
-    NB_CUDA(ctx, cudaMalloc(&g, len * 4));
+    if (cudaMalloc(&g, len * 4) != cudaSuccess) { cudaFree(f); cudaGetLastError(); return set_err(ctx, NB200_ERR_OOM, "circle tables"); }
     u32 thr = 256, blk = (u32)((len + thr - 1) / thr);
     circle_table_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_tw, 1u << ctx->tw.half_log, n, f);
     NB_LAUNCH_CHECK(ctx);
@@ -548,10 +461,10 @@ static nb200_status launch_tile(nb200_ctx* ctx, const FftPass& p) {
   constexpr int threads = 1 << (T - 4);
   static const size_t pad = getenv("NB200_FFT_PAD_SMEM") ? (size_t)atoi(getenv("NB200_FFT_PAD_SMEM")) * 1024 : 0;   // occupancy experiments
   const size_t smem = ((size_t)CB << (T + 2)) + pad;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[NB_MAX_DEVICES] = {false};   // cudaFuncSetAttribute is per device
+  if (!attr_set[ctx->device % NB_MAX_DEVICES]) {
     NB_CUDA(ctx, cudaFuncSetAttribute(fft_tile_kernel<INV, T, W, CB, NZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[ctx->device % NB_MAX_DEVICES] = true;
   }
   dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB - 1) / CB));
   fft_tile_kernel<INV, T, W, CB, NZ><<<grid, threads, smem, ctx->stream>>>(p);
@@ -588,7 +501,7 @@ static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* s
   p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
   p.tw_len = 1u << ctx->tw.half_log;
   const u32 *cf = nullptr, *ci = nullptr;
-  NB_TRY(circle_tables(ctx, p.tn, &cf, &ci));
+  NB_TRY(fft_circle_tables(ctx, p.tn, &cf, &ci));
   p.ctw2 = INV ? ci : cf;
   p.tw2 = INV ? ctx->tw.d_itw2 : ctx->tw.d_tw2;
   p.n_cols = (u32)n_cols; p.n = n; p.lo = pl.lo; p.T = pl.T; p.W = pl.W;
@@ -603,10 +516,10 @@ static nb200_status launch_pass(nb200_ctx* ctx, const PassPlan& pl, const u32* s
   u32 threads = 1u << (pl.T - 4);
   size_t smem = (size_t)p.cb << (pl.T + 2);
   dim3 grid(1u << (n - pl.T), (u32)((n_cols + p.cb - 1) / p.cb));
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[INV ? 1 : 0]) {
+  static bool attr_set[NB_MAX_DEVICES] = {false};   // one flag per (template instance, device)
+  if (!attr_set[ctx->device % NB_MAX_DEVICES]) {
     NB_CUDA(ctx, cudaFuncSetAttribute(fft_pass_kernel<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set[INV ? 1 : 0] = true;
+    attr_set[ctx->device % NB_MAX_DEVICES] = true;
   }
   fft_pass_kernel<INV><<<grid, threads, smem, ctx->stream>>>(p);
   NB_LAUNCH_CHECK(ctx);

@@ -88,15 +88,27 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
   if (max_log >= 1) NB_TRY(twiddles_prepare(ctx, max_log));
   trace_mark(ctx, nullptr);
   SchemeTree t;
+#define NB_TRYT(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) { free_tree(ctx, t); return _s; } } while (0)
   for (size_t b = 0; b < n; ++b) {
     nb200_cols *co = nullptr, *lde = nullptr;
-    NB_TRY(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size, &co));
+    NB_TRYT(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size, &co));
     t.coeffs.push_back(co);
-    NB_TRY(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size + s->log_blowup, &lde));
+    NB_TRYT(nb200_cols_alloc(ctx, evals[b]->n_cols, evals[b]->log_size + s->log_blowup, &lde));
     t.ldes.push_back(lde);
-    NB_TRY(fft_interpolate(ctx, evals[b]->d, co->d, co->n_cols, co->log_size));
-    NB_TRY(fft_evaluate(ctx, co->d, co->log_size, lde->d, lde->log_size, co->n_cols));
+    // when the AIR's degree bound says the quotient step will need these polynomials on the half coset D2 (component_quotients, Q_HALF),
+    // the fused pipeline emits them from the coefficient tiles it already holds in shared memory (if the memory is there)
+    nb200_cols* hx = nullptr;
+    const u32 lde_log = lde->log_size;
+    if (s->hint_log_expand == s->log_blowup + 1 && lde_log > 8) {
+      size_t free_b = 0, total_b = 0;
+      const size_t need = (co->n_cols << lde_log) * 4;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > need + ((size_t)24 << 30) && twiddles_prepare(ctx, lde_log + 1) == NB200_OK)
+        if (nb200_cols_alloc(ctx, co->n_cols, lde_log, &hx) != NB200_OK) hx = nullptr;
+    }
+    t.half_ext.push_back(hx);
+    NB_TRYT(commit_transforms(ctx, evals[b]->d, co->d, lde->d, hx ? hx->d : nullptr, co->n_cols, co->log_size, s->log_blowup));
   }
+#undef NB_TRYT
   trace_mark(ctx, "commit: ifft+lde");
   nb200_status st = finish_tree(ctx, t, ch);
   if (st != NB200_OK) { free_tree(ctx, t); return st; }
@@ -108,7 +120,7 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
 
 // The same, from HOST columns (the reference hands over host `Vec<BaseColumn>`s, trace_builder.rs:156-164): upload,
 // finalize_columns on the device when `coset_order`, transforms — pipelined chunk by chunk — then Merkle + mix_root.
-nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const size_t* n_cols, const u32* log_sizes, size_t n, int coset_order,
+nb200_status scheme_commit_host(nb200_scheme* s, const void* const* host, const u32* elem_bytes, const size_t* n_cols, const u32* log_sizes, size_t n, int coset_order,
                                 HostChannel& ch, uint8_t root[32], nb200_cols** evals_out) {
   nb200_ctx* ctx = s->ctx;
   u32 max_log = 0;
@@ -145,7 +157,7 @@ nb200_status scheme_commit_host(nb200_scheme* s, const u32* const* host, const s
     }
     t.half_ext.push_back(hx);
     NB_TRYC(upload_transform_pipelined(ctx, host[b], n_cols[b], log_sizes[b], coset_order, s->log_blowup, evals_out[b]->d, co->d, lde->d, hx ? hx->d : nullptr,
-                                       (long)b == leaf_batch ? &sink : nullptr));
+                                       (long)b == leaf_batch ? &sink : nullptr, elem_bytes ? elem_bytes[b] : 4u));
   }
 #undef NB_TRYC
   trace_mark(ctx, "commit(host): h2d+ifft+lde");
@@ -847,7 +859,14 @@ nb200_status nb200_scheme_commit(nb200_scheme* s, const nb200_cols* const* eval_
 nb200_status nb200_scheme_commit_host(nb200_scheme* s, const uint32_t* const* host_batches, const size_t* n_cols, const uint32_t* log_sizes, size_t n_batches,
                                       int coset_order, nb200_channel* channel, uint8_t root[32], nb200_cols** evals_out) {
   if (!s || !channel || !host_batches || !evals_out) return NB200_ERR_ARG;
-  return scheme_commit_host(s, host_batches, n_cols, log_sizes, n_batches, coset_order, channel->ch, root, evals_out);
+  return scheme_commit_host(s, (const void* const*)host_batches, nullptr, n_cols, log_sizes, n_batches, coset_order, channel->ch, root, evals_out);
+}
+nb200_status nb200_scheme_commit_host_packed(nb200_scheme* s, const void* const* host_batches, const uint32_t* elem_bytes, const size_t* n_cols, const uint32_t* log_sizes,
+                                             size_t n_batches, int coset_order, nb200_channel* channel, uint8_t root[32], nb200_cols** evals_out) {
+  if (!s || !channel || !host_batches || !evals_out) return NB200_ERR_ARG;
+  for (size_t b = 0; elem_bytes && b < n_batches; ++b)
+    if (!(elem_bytes[b] == 1 || elem_bytes[b] == 2 || elem_bytes[b] == 4)) return nb::set_err(s->ctx, NB200_ERR_ARG, "scheme_commit_host: 1, 2 or 4 bytes per host word");
+  return scheme_commit_host(s, host_batches, elem_bytes, n_cols, log_sizes, n_batches, coset_order, channel->ch, root, evals_out);
 }
 nb200_status nb200_gen_interaction_trace(nb200_ctx* ctx, const nb200_air* air, uint32_t component, const nb200_cols* const* tree0, size_t n0,
                                          const nb200_cols* const* tree1, size_t n1, const uint32_t* params, size_t n_params,

@@ -84,17 +84,25 @@ class AddMachine:
         """Columns of the main component in tree 1 (the multiplicity column of the table component comes after them)."""
         return 2 + 16 * self.n_lanes
 
-    def fill_main_trace(self, seed=0, n_padding=0, out=None):
+    def fill_main_trace(self, seed=0, n_padding=0, out=None, packed_out=None):
         """ADD chain: every lane adds two pseudo-random 32-bit words per row.  With `out` (an (n_main_columns, 2^log_size)
-        uint32 array, e.g. pinned memory from Context.host_alloc) the columns are written in place and `out` is returned."""
+        uint32 array, e.g. pinned memory from Context.host_alloc) the columns are written in place and `out` is returned.
+        With `packed_out` = (pc_block: (1, n) uint32, byte_block: (n_main_columns - 1, n) uint8) the trace is written in the
+        packed host format (nb200_scheme_commit_host_packed): every column but `pc` holds byte limbs / flags; the list
+        [pc_block, byte_block] is returned (commitment order is unchanged: 2-D blocks are consecutive columns)."""
         n = 1 << self.log_size
         rng = np.random.default_rng(seed)
 
         class _Sink(list):
             def append(self_inner, col):
-                if out is not None:
-                    out[len(self_inner)] = col
-                    col = out[len(self_inner)]
+                k = len(self_inner)
+                if packed_out is not None:
+                    dst = packed_out[0][0] if k == 0 else packed_out[1][k - 1]
+                    dst[:] = col
+                    col = dst
+                elif out is not None:
+                    out[k] = col
+                    col = out[k]
                 list.append(self_inner, col)
 
             def __iadd__(self_inner, more):
@@ -126,14 +134,18 @@ class AddMachine:
                 hist += np.bincount(x, minlength=256)
         assert len(cols) == self.air.n_columns()[1] - 1
         mult = (hist % P).astype(np.uint32)
+        if packed_out is not None:
+            return [packed_out[0], packed_out[1]], mult
         return (out if out is not None else list(cols)), mult
 
     def column_log_sizes(self):
         return self.air.column_log_sizes()
 
 
-def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
-    """The Machine::prove sequence (machine.rs:130-297) over `backend`.  Returns (proof_bytes, claimed_sums, aux)."""
+def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", resident=None):
+    """The Machine::prove sequence (machine.rs:130-297) over `backend`.  Returns (proof_bytes, claimed_sums, aux).
+    `resident` = (tree0 device batches, tree1 device batches) commits evaluations that are already on the device (finalized
+    order) instead of uploading `main_cols` — the HBM-resident variant bench.py's `value` times."""
     config = config or dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)
     air = machine.air
     ch = backend.channel()
@@ -144,10 +156,13 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b""):
         ch.mix_u64(ls)
     prover = backend.prover(machine.words, config)
     # tree 0: preprocessed (machine.rs:208-228)
-    roots = [prover.commit(machine.preprocessed_columns(), ch, coset_order=True)]
-    # tree 1: main trace + extension main columns (machine.rs:230-237)
-    main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)  # a 2-D block or a list of columns
-    roots.append(prover.commit(main_part + [mult], ch, coset_order=True))
+    if resident is not None:
+        roots = [prover.commit_batches(list(resident[0]), ch), prover.commit_batches(list(resident[1]), ch)]
+    else:
+        roots = [prover.commit(machine.preprocessed_columns(), ch, coset_order=True)]
+        # tree 1: main trace + extension main columns (machine.rs:230-237)
+        main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)  # a 2-D block or a list of columns / blocks
+        roots.append(prover.commit(main_part + [mult], ch, coset_order=True))
     # lookup elements (machine.rs:239-240)
     params = [(0, 0, 0, 0)] * air.n_params
     machine.range256.draw(ch, params)

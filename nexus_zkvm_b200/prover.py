@@ -129,7 +129,8 @@ class CommitmentSchemeProver:
             a = np.asarray(c)
             if a.ndim == 2:
                 flush()
-                out.append(np.ascontiguousarray(a, dtype=np.uint32))
+                # packed host formats: uint8 / uint16 blocks travel at their natural width and are widened on the device
+                out.append(np.ascontiguousarray(a) if a.dtype in (np.uint8, np.uint16, np.uint32) else np.ascontiguousarray(a, dtype=np.uint32))
             else:
                 a = np.ascontiguousarray(a, dtype=np.uint32)
                 if run and run[0].size != a.size:
@@ -142,12 +143,14 @@ class CommitmentSchemeProver:
         """tree_builder.extend_evals(host columns); commit(channel) — pipelined H2D + transforms (nb200_scheme_commit_host)."""
         hb = self._host_batches(cols)
         n = len(hb)
-        ptrs = (u32p * n)(*[b.ctypes.data_as(u32p) for b in hb])
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in hb])
+        widths = (C.c_uint32 * n)(*[b.dtype.itemsize for b in hb])
         ncols = (C.c_size_t * n)(*[b.shape[0] for b in hb])
         logs = (C.c_uint32 * n)(*[int(b.shape[1]).bit_length() - 1 for b in hb])
         evals = (C.c_void_p * n)()
         root = (C.c_uint8 * 32)()
-        self.ctx._chk(lib().nb200_scheme_commit_host(self._h, ptrs, ncols, logs, C.c_size_t(n), C.c_int(1 if coset_order else 0), ch._h, root, evals))
+        self.ctx._chk(lib().nb200_scheme_commit_host_packed(self._h, ptrs, widths, ncols, logs, C.c_size_t(n), C.c_int(1 if coset_order else 0), ch._h, root, evals))
+        self.h2d_bytes = getattr(self, "h2d_bytes", 0) + sum(b.nbytes for b in hb)
         self.ctx.sync()  # the host batches may be released by the caller after this returns
         self.tree_evals.append([Columns(self.ctx, C.c_void_p(evals[i])) for i in range(n)])
         return bytes(root)
