@@ -142,6 +142,32 @@ nb200_status nb200_commit_host_packed(nb200_ctx*, const void* const* host_batche
                                       const uint32_t* log_sizes, size_t n_batches, int coset_order, uint32_t log_blowup,
                                       nb200_cols** evals_io, nb200_cols** coeffs_io, nb200_cols** lde_io, nb200_tree** tree_out, uint8_t root[32]);
 
+/* ---- one commitment over N GPUs (one process per GPU, NCCL over NVLink inside the library) ------------------------
+ * The reference has no multi-device path; these entry points are what a multi-GPU `CudaBackend` would drive from
+ * TreeBuilder::commit (machine.rs:208-263).  Rank 0 creates the id and hands it to the other ranks out of band (MPI, a file,
+ * torch.distributed broadcast ...); world must be a power of two; NCCL is bound with dlopen (a libnccl already loaded into the
+ * process is shared). */
+size_t nb200_comm_unique_id_bytes(void);
+nb200_status nb200_comm_get_unique_id(uint8_t* id_out);
+nb200_status nb200_comm_init(nb200_ctx*, int rank, int world, const uint8_t* unique_id);
+void nb200_comm_destroy(nb200_ctx*);
+int nb200_comm_rank(const nb200_ctx*);
+int nb200_comm_world(const nb200_ctx*);
+/* the column range [first, first + count) of rank `rank`: contiguous, multiples of 16 columns (one Blake2s block) */
+nb200_status nb200_shard_range(size_t total_cols, int world, int rank, size_t* first, size_t* count);
+/* all-gather of a small host blob (Merkle caps, claimed sums, sampled values): out = world x bytes, rank order */
+nb200_status nb200_comm_all_gather(nb200_ctx*, const uint8_t* mine, size_t bytes, uint8_t* out);
+/* nb200_commit_evals of ONE tree by all ranks together: column-sharded fused iFFT+LDE -> NVLink exchange (grouped ncclSend/Recv of
+ * packed row slices) -> row-sharded sub-tree hashing -> ncclAllGather of the world caps -> top levels on the host.
+ * shard_evals = this rank's nb200_shard_range columns (2^log_size rows each; may be NULL when the range is empty);
+ * replicated = smaller batches that follow in commitment order, identical on every rank.
+ * Out: coefficients of this rank's columns, `rows` = ALL total_cols columns restricted to this rank's 2^(log_size+log_blowup)/world
+ * LDE rows (what row-sharded constraint / DEEP kernels consume), the rank's sub-tree, the caps (world x 32 bytes, may be NULL) and
+ * the root, bit-identical to the single-GPU root on every rank. */
+nb200_status nb200_commit_sharded(nb200_ctx*, const nb200_cols* shard_evals, size_t total_cols, uint32_t log_size, uint32_t log_blowup,
+                                  const nb200_cols* const* replicated, size_t n_replicated,
+                                  nb200_cols** coeffs_out, nb200_cols** rows_out, nb200_tree** subtree_out, uint8_t* caps_out, uint8_t root[32]);
+
 /* ---- Blake2sChannel (stwo core/channel/blake2s.rs; used at machine.rs:197-206,240,262) --------------- */
 /* The Fiat-Shamir transcript is sequential host work; it is part of the library so that the Rust shim and the
  * coarse nb200_prove share one implementation.  ctx may be NULL (defaults for the flavour switches). */

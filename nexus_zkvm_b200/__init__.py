@@ -236,6 +236,47 @@ class Context:
             ldes = [Columns(self, C.c_void_p(ld[i])) for i in range(n)]
         return evals, coeffs, ldes, MerkleTree(self, t, bytes(root), ldes)
 
+    # ---- multi-GPU (one process per GPU): NCCL communicator inside the library
+    @staticmethod
+    def comm_unique_id():
+        n = lib().nb200_comm_unique_id_bytes()
+        buf = (C.c_uint8 * n)()
+        if lib().nb200_comm_get_unique_id(buf) != 0:
+            raise Nb200Error("nb200_comm_get_unique_id failed: " + lib().nb200_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        self._chk(lib().nb200_comm_init(self._h, C.c_int(rank), C.c_int(world), (C.c_uint8 * len(unique_id)).from_buffer_copy(unique_id)))
+
+    def comm_init_from_torch(self, dist, device):
+        """Create the library's communicator for the ranks of a torch.distributed group (the id travels over that group)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        n = lib().nb200_comm_unique_id_bytes()
+        t = torch.zeros(n, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    @staticmethod
+    def shard_range(total_cols, world, rank):
+        f, c = C.c_size_t(), C.c_size_t()
+        assert lib().nb200_shard_range(C.c_size_t(total_cols), C.c_int(world), C.c_int(rank), C.byref(f), C.byref(c)) == 0
+        return int(f.value), int(c.value)
+
+    def commit_sharded(self, shard_evals, total_cols, log_size, log_blowup, replicated=()):
+        """nb200_commit_sharded: returns (coeffs of this rank's columns, row-slice batch of all columns, sub-tree, caps, root)."""
+        rep = (C.c_void_p * max(len(replicated), 1))(*[b._h for b in replicated])
+        co, rows, sub = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        world = lib().nb200_comm_world(self._h)
+        caps = (C.c_uint8 * (32 * world))()
+        root = (C.c_uint8 * 32)()
+        self._chk(lib().nb200_commit_sharded(self._h, shard_evals._h if shard_evals is not None else None, C.c_size_t(total_cols), C.c_uint32(log_size),
+                                             C.c_uint32(log_blowup), rep, C.c_size_t(len(replicated)), C.byref(co), C.byref(rows), C.byref(sub), caps, root))
+        rows_b = Columns(self, rows)
+        return Columns(self, co), rows_b, MerkleTree(self, sub, None, [rows_b]), [bytes(caps[32 * i:32 * i + 32]) for i in range(world)], bytes(root)
+
     def commit_evals(self, eval_batches, log_blowup, coeffs=None, ldes=None):
         """TreeBuilder.extend_evals(evals) + commit(): returns (coeff_batches, lde_batches, tree).
         `coeffs` / `ldes` may be batches from a previous call (reused, no allocation)."""

@@ -60,6 +60,7 @@ nb200_status nb200_ctx_create(int device, nb200_ctx** out) {
 void nb200_ctx_destroy(nb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  comm_release(ctx);
   fft_drop_tables(ctx);
   fft_fused_release(ctx);
   if (ctx->tw.d_tw) cudaFree(ctx->tw.d_tw);

@@ -117,6 +117,7 @@ nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst,
 // evaluations -> coefficients + LDE (+ optionally the half-coset extension the quotient step needs) for one batch (fft_fused.cu)
 nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 log_size, u32 log_blowup);
 void fft_fused_release(nb200_ctx* ctx);
+void comm_release(nb200_ctx* ctx);   // comm.cu
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
 nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32* dst, size_t n_cols, u32 log_size, int coset_order);
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)

@@ -182,8 +182,8 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
 // ================================================================================================================
 // A / C: one pass over a contiguous-or-strided tile with asynchronous staging (same work as fft.cu's fft_tile_kernel)
 // ================================================================================================================
-template <bool INV, int T, int W, int CB>
-__global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_tile_async_kernel(const FftPass p) {
+template <bool INV, int T, int W, int CB, int MINB>
+__global__ void __launch_bounds__(1 << (T - 4), MINB) fft_tile_async_kernel(const FftPass p) {
   extern __shared__ __align__(16) u32 sm[];
   constexpr int L = T - W;
   constexpr int NROUNDS = L / 4 + ((L % 4) ? 1 : 0);
@@ -221,8 +221,8 @@ struct FftMid {
   u32 fhi[4];                               // index of that block among the 2^n-word blocks of the forward transform (the bits above n)
 };
 
-template <int T, int W, int CB>
-__global__ void __launch_bounds__(1 << (T - 4), (T >= 13 ? 2 : 3)) fft_mid_kernel(const FftMid p) {
+template <int T, int W, int CB, int MINB>
+__global__ void __launch_bounds__(1 << (T - 4), MINB) fft_mid_kernel(const FftMid p) {
   extern __shared__ __align__(16) u32 sm[];
   constexpr int L = T - W;
   constexpr int NROUNDS = L / 4 + ((L % 4) ? 1 : 0);
@@ -273,7 +273,7 @@ static nb200_status set_smem(nb200_ctx* ctx, K kernel, size_t smem, bool* flags)
   return NB200_OK;
 }
 
-template <bool INV, int T, int CB>
+template <bool INV, int T, int CB, int MINB>
 static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t src_stride, u32* dst, size_t dst_stride, size_t n_cols, u32 n, u32 tn) {
   FftPass p;
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = (size_t)1 << n;
@@ -286,20 +286,20 @@ static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* sr
   p.n_cols = (u32)n_cols; p.n = n; p.lo = 0; p.T = T; p.W = 0; p.cb = CB; p.scale = 0; p.apply_scale = 0; p.tn = tn; p.ztop = n;
   constexpr size_t smem = (size_t)CB << (T + 2);
   static bool flags[NB_MAX_DEVICES] = {false};
-  NB_TRY(set_smem(ctx, fft_tile_async_kernel<INV, T, 0, CB>, smem, flags));
+  NB_TRY(set_smem(ctx, fft_tile_async_kernel<INV, T, 0, CB, MINB>, smem, flags));
   dim3 grid(1u << (n - T), (u32)((n_cols + CB - 1) / CB));
-  fft_tile_async_kernel<INV, T, 0, CB><<<grid, 1 << (T - 4), smem, st>>>(p);
+  fft_tile_async_kernel<INV, T, 0, CB, MINB><<<grid, 1 << (T - 4), smem, st>>>(p);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
 
-template <int T, int W, int CB>
+template <int T, int W, int CB, int MINB>
 static nb200_status launch_mid(nb200_ctx* ctx, cudaStream_t st, const FftMid& p) {
   constexpr size_t smem = (size_t)2 * CB << (T + 2);
   static bool flags[NB_MAX_DEVICES] = {false};
-  NB_TRY(set_smem(ctx, fft_mid_kernel<T, W, CB>, smem, flags));
+  NB_TRY(set_smem(ctx, fft_mid_kernel<T, W, CB, MINB>, smem, flags));
   dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB - 1) / CB));
-  fft_mid_kernel<T, W, CB><<<grid, 1 << (T - 4), smem, st>>>(p);
+  fft_mid_kernel<T, W, CB, MINB><<<grid, 1 << (T - 4), smem, st>>>(p);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
@@ -358,8 +358,12 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
     const u32* ev = evals + c0 * len;
     u32* co = coeffs + c0 * len;
     // A
-    if (pl.LA == 12) NB_TRY((launch_contig<true, 12, 4>(ctx, st, ev, len, co, len, nc, n, n)));
-    else NB_TRY((launch_contig<true, 13, 2>(ctx, st, ev, len, co, len, nc, n, n)));
+    static const int var_a = env_int("NB200_FFT_VAR_A", 0), var_b = env_int("NB200_FFT_VAR_B", 0), var_c = env_int("NB200_FFT_VAR_C", 0);   // tuning knobs (profiles/README.md)
+    if (pl.LA == 12) {
+      if (var_a == 1) NB_TRY((launch_contig<true, 12, 3, 4>(ctx, st, ev, len, co, len, nc, n, n)));
+      else if (var_a == 2) NB_TRY((launch_contig<true, 12, 2, 4>(ctx, st, ev, len, co, len, nc, n, n)));
+      else NB_TRY((launch_contig<true, 12, 4, 3>(ctx, st, ev, len, co, len, nc, n, n)));
+    } else NB_TRY((launch_contig<true, 13, 2, 2>(ctx, st, ev, len, co, len, nc, n, n)));
     // B
     FftMid p;
     p.src = co; p.src_stride = len; p.coeffs = co; p.coeff_stride = len;
@@ -375,22 +379,27 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
       }
     }
     switch (pl.Lm) {
-      case 4: NB_TRY((launch_mid<12, 8, 2>(ctx, st, p))); break;
-      case 5: NB_TRY((launch_mid<12, 7, 2>(ctx, st, p))); break;
-      case 6: NB_TRY((launch_mid<12, 6, 2>(ctx, st, p))); break;
-      case 7: NB_TRY((launch_mid<12, 5, 2>(ctx, st, p))); break;
-      case 8: NB_TRY((launch_mid<12, 4, 2>(ctx, st, p))); break;
-      case 9: NB_TRY((launch_mid<13, 4, 1>(ctx, st, p))); break;
+      case 4: NB_TRY((launch_mid<12, 8, 2, 3>(ctx, st, p))); break;
+      case 5: NB_TRY((launch_mid<12, 7, 2, 3>(ctx, st, p))); break;
+      case 6: NB_TRY((launch_mid<12, 6, 2, 3>(ctx, st, p))); break;
+      case 7: NB_TRY((launch_mid<12, 5, 2, 3>(ctx, st, p))); break;
+      case 8:
+        if (var_b == 1) NB_TRY((launch_mid<12, 4, 1, 4>(ctx, st, p)));
+        else NB_TRY((launch_mid<12, 4, 2, 3>(ctx, st, p)));
+        break;
+      case 9: NB_TRY((launch_mid<13, 4, 1, 2>(ctx, st, p))); break;
       default: return set_err(ctx, NB200_ERR_STATE, "commit transforms: plan");
     }
     // C: the contiguous low layers of every forward transform (each 2^n-word block is independent below layer n: run them as
     // one launch over the 2^m-word columns)
-    if (pl.LA == 12) NB_TRY((launch_contig<false, 12, 4>(ctx, st, lde + c0 * mlen, mlen, lde + c0 * mlen, mlen, nc, m, m)));
-    else NB_TRY((launch_contig<false, 13, 2>(ctx, st, lde + c0 * mlen, mlen, lde + c0 * mlen, mlen, nc, m, m)));
-    if (half_ext) {
-      if (pl.LA == 12) NB_TRY((launch_contig<false, 12, 4>(ctx, st, half_ext + c0 * mlen, mlen, half_ext + c0 * mlen, mlen, nc, m, m + 1)));
-      else NB_TRY((launch_contig<false, 13, 2>(ctx, st, half_ext + c0 * mlen, mlen, half_ext + c0 * mlen, mlen, nc, m, m + 1)));
-    }
+    auto fwd_low = [&](u32* buf, u32 tn) -> nb200_status {
+      if (pl.LA != 12) return launch_contig<false, 13, 2, 2>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+      if (var_c == 1) return launch_contig<false, 12, 3, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+      if (var_c == 2) return launch_contig<false, 12, 2, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+      return launch_contig<false, 12, 4, 3>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+    };
+    NB_TRY(fwd_low(lde + c0 * mlen, m));
+    if (half_ext) NB_TRY(fwd_low(half_ext + c0 * mlen, m + 1));
   }
   if (multi) {
     for (int i = 0; i < 2; ++i) {

@@ -69,6 +69,18 @@ extern "C" {
     pub fn nb200_commit_host_packed(ctx: *mut nb200_ctx, host_batches: *const *const c_void, elem_bytes: *const u32, n_cols: *const usize,
                                     log_sizes: *const u32, n_batches: usize, coset_order: c_int, log_blowup: u32, evals_io: *mut *mut nb200_cols,
                                     coeffs_io: *mut *mut nb200_cols, lde_io: *mut *mut nb200_cols, tree_out: *mut *mut nb200_tree, root: *mut u8) -> c_int;
+    // ---- one commitment over N GPUs (NCCL inside the library)
+    pub fn nb200_comm_unique_id_bytes() -> usize;
+    pub fn nb200_comm_get_unique_id(id_out: *mut u8) -> c_int;
+    pub fn nb200_comm_init(ctx: *mut nb200_ctx, rank: c_int, world: c_int, unique_id: *const u8) -> c_int;
+    pub fn nb200_comm_destroy(ctx: *mut nb200_ctx);
+    pub fn nb200_comm_rank(ctx: *const nb200_ctx) -> c_int;
+    pub fn nb200_comm_world(ctx: *const nb200_ctx) -> c_int;
+    pub fn nb200_shard_range(total_cols: usize, world: c_int, rank: c_int, first: *mut usize, count: *mut usize) -> c_int;
+    pub fn nb200_comm_all_gather(ctx: *mut nb200_ctx, mine: *const u8, bytes: usize, out: *mut u8) -> c_int;
+    pub fn nb200_commit_sharded(ctx: *mut nb200_ctx, shard_evals: *const nb200_cols, total_cols: usize, log_size: u32, log_blowup: u32,
+                                replicated: *const *const nb200_cols, n_replicated: usize, coeffs_out: *mut *mut nb200_cols, rows_out: *mut *mut nb200_cols,
+                                subtree_out: *mut *mut nb200_tree, caps_out: *mut u8, root: *mut u8) -> c_int;
     // ---- Blake2sChannel
     pub fn nb200_channel_new(ctx: *mut nb200_ctx, out: *mut *mut nb200_channel) -> c_int;
     pub fn nb200_channel_clone(ch: *const nb200_channel, out: *mut *mut nb200_channel) -> c_int;

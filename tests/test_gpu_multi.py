@@ -41,6 +41,64 @@ def _worker(rank, world, port, n_cols, log_size, q):
         dist.destroy_process_group()
 
 
+def _lib_worker(rank, world, port, n_cols, log_size, small, q):
+    """The in-library path: nb200_comm_init + nb200_commit_sharded (NCCL inside libnexus_b200.so, no torch collectives on the data path)."""
+    import torch
+    import torch.distributed as dist
+    import nexus_zkvm_b200 as nb
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ctx = nb.Context(rank)      # its own non-blocking stream: nothing here depends on torch's stream
+        ctx.comm_init_from_torch(dist, torch.device("cuda", rank))
+        rng = np.random.default_rng(7)
+        full = rng.integers(0, P, (n_cols, 1 << log_size), dtype=np.uint32)
+        smalls = [rng.integers(0, P, (nc, 1 << lg), dtype=np.uint32) for nc, lg in small]
+        first, count = nb.Context.shard_range(n_cols, world, rank)
+        shard = ctx.upload(full[first:first + count]) if count else None
+        rep = [ctx.upload(s) for s in smalls]
+        co, rows, sub, caps, root = ctx.commit_sharded(shard, n_cols, log_size, 1, rep)
+        ok_coeffs = True
+        single = None
+        if rank == 0:
+            ev = [ctx.upload(full)] + [ctx.upload(s) for s in smalls]
+            coeffs1, ldes1, tree = ctx.commit_evals(ev, 1)
+            single = tree.root
+            ok_coeffs = bool(np.array_equal(co.download(), coeffs1[0].download()[first:first + count]))
+            # the row-slice batch holds every column's rows [rank * S, (rank + 1) * S)
+            S = (1 << (log_size + 1)) // world
+            ok_coeffs = ok_coeffs and bool(np.array_equal(rows.download(), ldes1[0].download()[:, rank * S:(rank + 1) * S]))
+        q.put((rank, root, single, ok_coeffs, caps))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cols,log_size,small", [(50, 12, []), (339, 14, [(1, 8)]), (1012, 13, [(4, 8), (3, 0)])])
+def test_library_sharded_commit_matches_single_gpu_root(n_cols, log_size, small):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lib_worker, args=(r, world, port, n_cols, log_size, small, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = [s for _, _, s, _, _ in res if s is not None][0]
+    for rank, root, _, ok, caps in res:
+        assert root == single, f"rank {rank}"
+        assert ok and len(caps) == world
+
+
 @pytest.mark.parametrize("n_cols,log_size", [(50, 12), (1386, 14)])
 def test_sharded_commit_matches_single_gpu_root(n_cols, log_size):
     import torch
