@@ -73,8 +73,12 @@ def build(force=False, verbose=False):
 # ---- cubin cache for the run-time specialised AIR kernels (csrc/jit.cu) ---------------------------------------------
 JIT_CACHE = os.path.join(HERE, "jit_cache")
 # (log_size, n_lanes, logup_in_pairs): bench.py / tools/prove_trace.py, __graft_entry__.smoke and the machines of tests/test_gpu_*.py
-SHIPPED_MACHINES = [(20, 21, False), (16, 21, False), (8, 1, False), (8, 2, False), (8, 2, True), (8, 3, False), (9, 1, False), (9, 2, False),
+SHIPPED_MACHINES = [(20, 21, False), (22, 21, False), (16, 21, False), (8, 1, False), (8, 2, False), (8, 2, True), (8, 3, False), (9, 1, False), (9, 2, False),
                     (9, 2, True), (10, 1, False), (12, 3, False)]
+
+
+# prover2-shaped machines (machine.MultiMachine) of tests/test_gpu_prove_parity.py and bench.py --multi: component log sizes
+SHIPPED_MULTI = [list(range(4, 12)), list(range(4, 18)), list(range(4, 22))]
 
 
 def kernel_sources(words):
@@ -110,8 +114,9 @@ def precompile_kernels(machines=SHIPPED_MACHINES, verbose=False):
     from . import machine as M
     os.makedirs(JIT_CACHE, exist_ok=True)
     todo = {}
-    for log_size, lanes, pairs in machines:
-        m = M.AddMachine(log_size=log_size, n_lanes=lanes, logup_in_pairs=pairs)
+    ms = [M.AddMachine(log_size=log_size, n_lanes=lanes, logup_in_pairs=pairs) for log_size, lanes, pairs in machines]
+    ms += [M.MultiMachine(sizes) for sizes in SHIPPED_MULTI]
+    for m in ms:
         for key, src in kernel_sources(m.words):
             path = os.path.join(JIT_CACHE, f"{key:016x}.cubin")
             if not os.path.exists(path):

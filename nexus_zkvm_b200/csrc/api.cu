@@ -67,6 +67,8 @@ void nb200_ctx_destroy(nb200_ctx* ctx) {
   if (ctx->tw.d_itw) cudaFree(ctx->tw.d_itw);
   if (ctx->tw.d_tw2) cudaFree(ctx->tw.d_tw2);
   if (ctx->tw.d_itw2) cudaFree(ctx->tw.d_itw2);
+  if (ctx->tw.d_ptw2) cudaFree(ctx->tw.d_ptw2);
+  if (ctx->tw.d_iptw2) cudaFree(ctx->tw.d_iptw2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->copy_stream) {
     cudaStreamDestroy(ctx->copy_stream);

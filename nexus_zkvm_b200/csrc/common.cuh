@@ -16,6 +16,9 @@ struct TwiddleBank {
   u32* d_itw = nullptr;   // element-wise inverses
   u32* d_tw2 = nullptr;   // 2 * twiddle (< 2^32): the FFT's Mersenne multiply wants the doubled constant (m31_mul_dbl)
   u32* d_itw2 = nullptr;  // 2 * inverse twiddle
+  // product banks for the radix-4 steps (fft_common.cuh radix16p): entry j of layer l = 2 * (t_l[j] * t_{l+1}[j >> 1]), negated for odd j
+  u32* d_ptw2 = nullptr;
+  u32* d_iptw2 = nullptr;
 };
 
 }  // namespace nb

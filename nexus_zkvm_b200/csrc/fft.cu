@@ -403,11 +403,22 @@ nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32
 }
 
 // ---- circle-twiddle tables (layer 0 of each transform size), owned by the ctx (freed in nb200_ctx_destroy) ----
-struct CircleTables { std::map<u32, std::pair<u32*, u32*>> by_log; };
+struct CircleTables { std::map<u32, std::pair<u32*, u32*>> by_log, prod_by_log; };
+// doubled product of the circle twiddle h with line layer 1's twiddle h >> 1 (negated for odd h): the radix-4 pairing of layers (1, 0)
+__global__ void circle_product_kernel(const u32* __restrict__ tw, u32 tw_len, u32 n, u32* __restrict__ out) {
+  u32 h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= (1u << (n - 1))) return;
+  u32 c = circle_tw(tw, tw_len, n, h);
+  u32 l1 = (n >= 2) ? line_tw(tw, tw_len, n, 1, h >> 1) : 1u;
+  u32 p = m31_mul(c, l1);
+  if (h & 1u) p = m31_neg(p);
+  out[h] = p << 1;
+}
 void fft_drop_tables(nb200_ctx* ctx) {
   CircleTables* ct = (CircleTables*)ctx->fft_tables;
   if (!ct) return;
   for (auto& kv : ct->by_log) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+  for (auto& kv : ct->prod_by_log) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
   delete ct;
   ctx->fft_tables = nullptr;
 }
@@ -426,6 +437,26 @@ nb200_status fft_circle_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32
     circle_table_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_itw, 1u << ctx->tw.half_log, n, g);
     NB_LAUNCH_CHECK(ctx);
     it = ct.by_log.emplace(n, std::make_pair(f, g)).first;
+  }
+  *fwd = it->second.first; *inv = it->second.second;
+  return NB200_OK;
+}
+
+nb200_status fft_circle_product_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv) {
+  if (!ctx->fft_tables) ctx->fft_tables = new CircleTables();
+  CircleTables& ct = *(CircleTables*)ctx->fft_tables;
+  auto it = ct.prod_by_log.find(n);
+  if (it == ct.prod_by_log.end()) {
+    u32 *f = nullptr, *g = nullptr;
+    size_t len = (size_t)1 << (n - 1);
+    NB_CUDA(ctx, cudaMalloc(&f, len * 4));
+    if (cudaMalloc(&g, len * 4) != cudaSuccess) { cudaFree(f); cudaGetLastError(); return set_err(ctx, NB200_ERR_OOM, "circle product tables"); }
+    u32 thr = 256, blk = (u32)((len + thr - 1) / thr);
+    circle_product_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_tw, 1u << ctx->tw.half_log, n, f);
+    NB_LAUNCH_CHECK(ctx);
+    circle_product_kernel<<<blk, thr, 0, ctx->stream>>>(ctx->tw.d_itw, 1u << ctx->tw.half_log, n, g);
+    NB_LAUNCH_CHECK(ctx);
+    it = ct.prod_by_log.emplace(n, std::make_pair(f, g)).first;
   }
   *fwd = it->second.first; *inv = it->second.second;
   return NB200_OK;

@@ -108,6 +108,51 @@ __device__ __forceinline__ void radix16(u32 (&v)[16], const u32 (&tw)[15], const
 }
 
 
+// a*ta + b*tb mod P with both constants pre-doubled: the two 64-bit products (each < 2^63) are summed BEFORE the Mersenne fold, so a
+// radix-4 step needs one fold for t*(v1 +- s*v3) = t*v1 +- (t*s)*v3 instead of two butterflies' worth (fft_fused.cu, radix16p).
+__device__ __forceinline__ u32 m31_mul2_dbl(u32 a, u32 ta2, u32 b, u32 tb2) {
+  const u64 p = (u64)a * ta2 + (u64)b * tb2;   // = 2 X, X = a*ta + b*tb < 2 P^2
+  u32 hi = (u32)(p >> 32);                      // X >> 31 < 2 P
+  hi = umin32(hi, hi - P31);
+  const u32 s = ((u32)p >> 1) + hi;             // (X mod 2^31) + (X >> 31 mod P) <= 2 P
+  return umin32(s, s - P31);
+}
+
+// One radix-16 round (4 layers) as two radix-4 steps with PRODUCT twiddles: for the layer pair (j+1, j) with twiddles s (layer j+1), t_a / t_b
+// (layer j, even / odd index) the table holds pt_a = t_a*s and pt_b = P - t_b*s (doubled).  Forward:  t_a*(v1 + s*v3) = t_a*v1 + pt_a*v3 and
+// t_b*(v1 - s*v3) = t_b*v1 + pt_b*v3; inverse:  ia*(v0-v1) + ib*(v2-v3)  and  is*(ia*(v0-v1) - ib*(v2-v3)) = pia*(v0-v1) + pib*(v2-v3).
+// 25 instructions (14 on the ALU pipe) per four butterflies instead of 28 (16): field arithmetic is exact, so the results are identical.
+// tw: as radix16 (15 doubled twiddles); pt[0..7]: products of layer 0 with layer 1, pt[8..9]: of layer 2 with layer 3.
+template <bool INV>
+__device__ __forceinline__ void radix4p(u32& v0, u32& v1, u32& v2, u32& v3, const u32 ta, const u32 tb, const u32 s, const u32 pa, const u32 pb) {
+  if (!INV) {
+    const u32 tmp = m31_mul_dbl(v2, s);
+    const u32 a0 = m31_add(v0, tmp), a2 = m31_sub(v0, tmp);
+    const u32 b1 = m31_mul2_dbl(v1, ta, v3, pa), b3 = m31_mul2_dbl(v1, tb, v3, pb);
+    v0 = m31_add(a0, b1); v1 = m31_sub(a0, b1); v2 = m31_add(a2, b3); v3 = m31_sub(a2, b3);
+  } else {
+    const u32 d01 = m31_sub(v0, v1), d23 = m31_sub(v2, v3), b0 = m31_add(v0, v1), b2 = m31_add(v2, v3);
+    v0 = m31_add(b0, b2);
+    v2 = m31_mul_dbl(m31_sub(b0, b2), s);
+    v1 = m31_mul2_dbl(d01, ta, d23, tb);
+    v3 = m31_mul2_dbl(d01, pa, d23, pb);
+  }
+}
+template <bool INV>
+__device__ __forceinline__ void radix16p(u32 (&v)[16], const u32 (&tw)[15], const u32 (&pt)[10]) {
+  if (INV) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) radix4p<true>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], tw[2 * g], tw[2 * g + 1], tw[8 + g], pt[2 * g], pt[2 * g + 1]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) radix4p<true>(v[r], v[r + 4], v[r + 8], v[r + 12], tw[12], tw[13], tw[14], pt[8], pt[9]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) radix4p<false>(v[r], v[r + 4], v[r + 8], v[r + 12], tw[12], tw[13], tw[14], pt[8], pt[9]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) radix4p<false>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], tw[2 * g], tw[2 * g + 1], tw[8 + g], pt[2 * g], pt[2 * g + 1]);
+  }
+}
+
 // ---- asynchronous global -> shared copies (LDGSTS): no registers, no issue slots between request and use ----
 __device__ __forceinline__ void cp_async16(u32 smem_addr, const void* g, bool valid) {
   const int sz = valid ? 16 : 0;   // src-size 0: nothing is read, the 16 bytes are zero-filled
@@ -119,5 +164,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // circle (layer 0) twiddle tables of a transform size, cached per ctx (fft.cu)
 nb200_status fft_circle_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv);
+// the product tables of the circle layer with line layer 1 (radix16p), same indexing as the circle tables
+nb200_status fft_circle_product_tables(nb200_ctx* ctx, u32 n, const u32** fwd, const u32** inv);
 
 }  // namespace nb

@@ -93,9 +93,11 @@ __device__ __forceinline__ void stage_out(const TileGeo<T, W>& geo, const u32* s
 // One radix-16 round (<= 4 butterfly layers) over the CB column tiles of a CTA: column c is read at sm_src + c*2^T and written at
 // sm_dst + c*2^T (equal pointers = in place).  RI = position of the round inside the pass (0 = lowest layers), as in fft.cu.
 // SCALE: multiply the outputs by sc2/2 (the 2^-n of interpolate).  WAITC: this is the first round after an asynchronous stage-in.
-template <bool INV, int T, int W, int CB, int RI, bool SCALE, bool WAITC, int NZ>
+// PROD: full 4-layer rounds run as two radix-4 steps with product twiddles (fft_common.cuh radix16p; ptw2 / cptw2 = product bank / circle product table).
+template <bool INV, int T, int W, int CB, int RI, bool SCALE, bool WAITC, int NZ, bool PROD = false>
 __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u32* __restrict__ ctw2, const u32 tw_len, const u32 tn, const u32 lo,
-                                           const u32 tile_hi, const u32* sm_src, u32* sm_dst, const u32 ncb, const u32 sc2) {
+                                           const u32 tile_hi, const u32* sm_src, u32* sm_dst, const u32 ncb, const u32 sc2,
+                                           const u32* __restrict__ ptw2 = nullptr, const u32* __restrict__ cptw2 = nullptr) {
   constexpr int L = T - W, NFULL = L / 4, REM = L % 4;
   constexpr int b = RI < NFULL ? W + 4 * RI : T - 4;
   constexpr int jlo = RI < NFULL ? 0 : 4 - REM;
@@ -128,6 +130,21 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
       }
     }
   }
+  constexpr bool USEP = PROD && jlo == 0 && NZ == 0;
+  u32 pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (USEP) {
+    {
+      const u32 hbase = (tile_hi << (L - (b - W) - 1)) | (tau_hi << 3);
+      const u32* __restrict__ src = (W == 0 && b == 0) ? (cptw2 + hbase) : (ptw2 + (tw_len - (1u << (tn - (lo + b - W)))) + hbase);
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), c4 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+      pt[0] = a.x; pt[1] = a.y; pt[2] = a.z; pt[3] = a.w; pt[4] = c4.x; pt[5] = c4.y; pt[6] = c4.z; pt[7] = c4.w;
+    }
+    {
+      const u32 hbase = (tile_hi << (L - (b + 2 - W) - 1)) | (tau_hi << 1);
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(ptw2 + (tw_len - (1u << (tn - (lo + b + 2 - W)))) + hbase));
+      pt[8] = a.x; pt[9] = a.y;
+    }
+  }
   const u32 sbase = (tau_hi << (b + 4)) | tau_lo;
   if (b == 0) {
     // the 16 words of a thread are contiguous: 4 x 128-bit shared accesses
@@ -143,7 +160,7 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
         uint4 q2 = *reinterpret_cast<const uint4*>(sc + a2), q3 = *reinterpret_cast<const uint4*>(sc + a3);
         v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
         v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w; v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
-        radix16<INV>(v, tw, jlo, triv);
+        if (USEP) radix16p<INV>(v, tw, pt); else radix16<INV>(v, tw, jlo, triv);
         if (SCALE) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = m31_mul_dbl(v[k], sc2);
@@ -157,7 +174,10 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
   } else {
     u32 addr[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) addr[k] = swz2(sbase | ((u32)k << b));
+    for (int k = 0; k < 16; ++k) {
+      addr[k] = swz2(sbase | ((u32)k << b));
+      if (PROD) asm volatile("" : "+r"(addr[k]));   // keep the 16 addresses live across the columns (ptxas otherwise rematerialises them per column: +300 ALU-pipe instructions)
+    }
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
       if (WAITC) { wait_column<CB>(c); __syncthreads(); }
@@ -167,7 +187,7 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
         u32 v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = sc[addr[k]];
-        radix16<INV>(v, tw, jlo, triv);
+        if (USEP) radix16p<INV>(v, tw, pt); else radix16<INV>(v, tw, jlo, triv);
         if (SCALE) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] = m31_mul_dbl(v[k], sc2);
@@ -182,8 +202,8 @@ __device__ __forceinline__ void tile_round(const u32* __restrict__ tw2, const u3
 // ================================================================================================================
 // A / C: one pass over a contiguous-or-strided tile with asynchronous staging (same work as fft.cu's fft_tile_kernel)
 // ================================================================================================================
-template <bool INV, int T, int W, int CB, int MINB>
-__global__ void __launch_bounds__(1 << (T - 4), MINB) fft_tile_async_kernel(const FftPass p) {
+template <bool INV, int T, int W, int CB, int MINB, bool PROD>
+__global__ void __launch_bounds__(1 << (T - 4), MINB) fft_tile_async_kernel(const FftPass p, const u32* __restrict__ ptw2, const u32* __restrict__ cptw2) {
   extern __shared__ __align__(16) u32 sm[];
   constexpr int L = T - W;
   constexpr int NROUNDS = L / 4 + ((L % 4) ? 1 : 0);
@@ -200,7 +220,7 @@ __global__ void __launch_bounds__(1 << (T - 4), MINB) fft_tile_async_kernel(cons
   static_for<0, NROUNDS>([&](auto rr) {   // (the 2^-n scaling of interpolate is applied by fft_mid_kernel)
     constexpr int RR = decltype(rr)::value;
     constexpr int RI = INV ? RR : NROUNDS - 1 - RR;
-    tile_round<INV, T, W, CB, RI, false, RR == 0, 0>(p.tw2, p.ctw2, p.tw_len, p.tn, lo, tile_hi, sm, sm, ncb, 0u);
+    tile_round<INV, T, W, CB, RI, false, RR == 0, 0, PROD>(p.tw2, p.ctw2, p.tw_len, p.tn, lo, tile_hi, sm, sm, ncb, 0u, ptw2, cptw2);
     __syncthreads();
   });
   stage_out<T, W, CB>(geo, sm, p.dst, p.dst_stride, col0, ncb);
@@ -213,6 +233,7 @@ struct FftMid {
   const u32* src; size_t src_stride;        // A's output: 2^n words per column
   u32* coeffs; size_t coeff_stride;         // coefficients out (may alias src: a CTA reads its tile completely before it writes)
   const u32* itw2; const u32* tw2; u32 tw_len;
+  const u32* iptw2; const u32* ptw2;        // product banks (radix16p)
   u32 n_cols, n, lo;                        // this pass owns inverse layers [lo, n)
   u32 sc2;                                  // 2 * 2^-n (doubled for m31_mul_dbl)
   u32 nfwd;                                 // forward heads to run (<= 4)
@@ -221,7 +242,7 @@ struct FftMid {
   u32 fhi[4];                               // index of that block among the 2^n-word blocks of the forward transform (the bits above n)
 };
 
-template <int T, int W, int CB, int MINB>
+template <int T, int W, int CB, int MINB, bool PROD>
 __global__ void __launch_bounds__(1 << (T - 4), MINB) fft_mid_kernel(const FftMid p) {
   extern __shared__ __align__(16) u32 sm[];
   constexpr int L = T - W;
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(1 << (T - 4), MINB) fft_mid_kernel(const FftMi
   // ---- inverse layers lo..n-1, scaled: S0 = coefficients
   static_for<0, NROUNDS>([&](auto rr) {
     constexpr int RR = decltype(rr)::value;
-    tile_round<true, T, W, CB, RR, RR == NROUNDS - 1, RR == 0, 0>(p.itw2, nullptr, p.tw_len, p.n, lo, tile_hi, S0, S0, ncb, p.sc2);
+    tile_round<true, T, W, CB, RR, RR == NROUNDS - 1, RR == 0, 0, PROD>(p.itw2, nullptr, p.tw_len, p.n, lo, tile_hi, S0, S0, ncb, p.sc2, p.iptw2, nullptr);
     __syncthreads();
   });
   stage_out<T, W, CB>(geo, S0, p.coeffs, p.coeff_stride, col0, ncb);
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(1 << (T - 4), MINB) fft_mid_kernel(const FftMi
     static_for<0, NROUNDS>([&](auto rr) {
       constexpr int RR = decltype(rr)::value;
       constexpr int RI = NROUNDS - 1 - RR;
-      tile_round<false, T, W, CB, RI, false, false, 0>(p.tw2, nullptr, p.tw_len, ftn, lo, fhi, RR == 0 ? S0 : S1, S1, ncb, 0u);
+      tile_round<false, T, W, CB, RI, false, false, 0, PROD>(p.tw2, nullptr, p.tw_len, ftn, lo, fhi, RR == 0 ? S0 : S1, S1, ncb, 0u, p.ptw2, nullptr);
       __syncthreads();
     });
     stage_out<T, W, CB>(geo, S1, p.fdst[f], p.fstride[f], col0, ncb);
@@ -273,7 +294,7 @@ static nb200_status set_smem(nb200_ctx* ctx, K kernel, size_t smem, bool* flags)
   return NB200_OK;
 }
 
-template <bool INV, int T, int CB, int MINB>
+template <bool INV, int T, int CB, int MINB, bool PROD = false>
 static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t src_stride, u32* dst, size_t dst_stride, size_t n_cols, u32 n, u32 tn) {
   FftPass p;
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = (size_t)1 << n;
@@ -286,20 +307,22 @@ static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* sr
   p.n_cols = (u32)n_cols; p.n = n; p.lo = 0; p.T = T; p.W = 0; p.cb = CB; p.scale = 0; p.apply_scale = 0; p.tn = tn; p.ztop = n;
   constexpr size_t smem = (size_t)CB << (T + 2);
   static bool flags[NB_MAX_DEVICES] = {false};
-  NB_TRY(set_smem(ctx, fft_tile_async_kernel<INV, T, 0, CB, MINB>, smem, flags));
+  const u32 *pf = nullptr, *pi = nullptr;
+  if (PROD) NB_TRY(fft_circle_product_tables(ctx, tn, &pf, &pi));
+  NB_TRY(set_smem(ctx, fft_tile_async_kernel<INV, T, 0, CB, MINB, PROD>, smem, flags));
   dim3 grid(1u << (n - T), (u32)((n_cols + CB - 1) / CB));
-  fft_tile_async_kernel<INV, T, 0, CB, MINB><<<grid, 1 << (T - 4), smem, st>>>(p);
+  fft_tile_async_kernel<INV, T, 0, CB, MINB, PROD><<<grid, 1 << (T - 4), smem, st>>>(p, INV ? ctx->tw.d_iptw2 : ctx->tw.d_ptw2, INV ? pi : pf);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
 
-template <int T, int W, int CB, int MINB>
+template <int T, int W, int CB, int MINB, bool PROD = false>
 static nb200_status launch_mid(nb200_ctx* ctx, cudaStream_t st, const FftMid& p) {
   constexpr size_t smem = (size_t)2 * CB << (T + 2);
   static bool flags[NB_MAX_DEVICES] = {false};
-  NB_TRY(set_smem(ctx, fft_mid_kernel<T, W, CB, MINB>, smem, flags));
+  NB_TRY(set_smem(ctx, fft_mid_kernel<T, W, CB, MINB, PROD>, smem, flags));
   dim3 grid(1u << (p.n - T), (u32)((p.n_cols + CB - 1) / CB));
-  fft_mid_kernel<T, W, CB, MINB><<<grid, 1 << (T - 4), smem, st>>>(p);
+  fft_mid_kernel<T, W, CB, MINB, PROD><<<grid, 1 << (T - 4), smem, st>>>(p);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }
@@ -362,12 +385,14 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
     if (pl.LA == 12) {
       if (var_a == 1) NB_TRY((launch_contig<true, 12, 3, 4>(ctx, st, ev, len, co, len, nc, n, n)));
       else if (var_a == 2) NB_TRY((launch_contig<true, 12, 2, 4>(ctx, st, ev, len, co, len, nc, n, n)));
+      else if (var_a == 3) NB_TRY((launch_contig<true, 12, 4, 3, true>(ctx, st, ev, len, co, len, nc, n, n)));
       else NB_TRY((launch_contig<true, 12, 4, 3>(ctx, st, ev, len, co, len, nc, n, n)));
     } else NB_TRY((launch_contig<true, 13, 2, 2>(ctx, st, ev, len, co, len, nc, n, n)));
     // B
     FftMid p;
     p.src = co; p.src_stride = len; p.coeffs = co; p.coeff_stride = len;
     p.itw2 = ctx->tw.d_itw2; p.tw2 = ctx->tw.d_tw2; p.tw_len = 1u << ctx->tw.half_log;
+    p.iptw2 = ctx->tw.d_iptw2; p.ptw2 = ctx->tw.d_ptw2;
     p.n_cols = (u32)nc; p.n = n; p.lo = pl.LA; p.sc2 = sc << 1;
     p.nfwd = 0;
     for (u32 r = 0; r < (1u << bl); ++r) {
@@ -385,6 +410,7 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
       case 7: NB_TRY((launch_mid<12, 5, 2, 3>(ctx, st, p))); break;
       case 8:
         if (var_b == 1) NB_TRY((launch_mid<12, 4, 1, 4>(ctx, st, p)));
+        else if (var_b == 3) NB_TRY((launch_mid<12, 4, 2, 3, true>(ctx, st, p)));
         else NB_TRY((launch_mid<12, 4, 2, 3>(ctx, st, p)));
         break;
       case 9: NB_TRY((launch_mid<13, 4, 1, 2>(ctx, st, p))); break;
@@ -396,6 +422,7 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
       if (pl.LA != 12) return launch_contig<false, 13, 2, 2>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
       if (var_c == 1) return launch_contig<false, 12, 3, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
       if (var_c == 2) return launch_contig<false, 12, 2, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+      if (var_c == 3) return launch_contig<false, 12, 4, 3, true>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
       return launch_contig<false, 12, 4, 3>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
     };
     NB_TRY(fwd_low(lde + c0 * mlen, m));

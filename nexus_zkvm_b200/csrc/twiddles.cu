@@ -46,13 +46,30 @@ __global__ void twiddle_bank_kernel(u32* __restrict__ tw, u32* __restrict__ itw,
   tw[e] = x; itw[e] = xi; tw2[e] = x << 1; itw2[e] = xi << 1;
 }
 
+// product bank: element e of layer l (index j inside the layer) times element j >> 1 of layer l + 1; odd j negated; doubled
+__global__ void twiddle_product_kernel(const u32* __restrict__ tw, u32* __restrict__ out, u32 k) {
+  u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 len = 1u << k;
+  if (e >= len) return;
+  u32 m = len - e;                       // in [1, 2^k]
+  u32 cl = (m == 1) ? 0 : 32 - __clz(m - 1);
+  if (cl == 0) { out[e] = tw[e] << 1; return; }   // pad word
+  u32 off = len - (1u << cl);            // start of this layer: 2^(cl-1) entries
+  u32 j = e - off;
+  u32 noff = len - (1u << (cl - 1));     // start of the next layer (or the pad)
+  u32 nxt = (cl - 1 == 0) ? tw[len - 1] : tw[noff + (j >> 1)];
+  u32 p = m31_mul(tw[e], nxt);
+  if (j & 1u) p = m31_neg(p);
+  out[e] = p << 1;
+}
+
 nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log) {
   NB_ARG(ctx, max_domain_log >= 1 && max_domain_log <= 30, "twiddles: domain log out of range");
   u32 k = max_domain_log - 1;
   if (ctx->tw.d_tw && ctx->tw.half_log >= k) return NB200_OK;
   if (ctx->tw.d_tw) {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->tw.d_tw); cudaFree(ctx->tw.d_itw); cudaFree(ctx->tw.d_tw2); cudaFree(ctx->tw.d_itw2);
+    cudaFree(ctx->tw.d_tw); cudaFree(ctx->tw.d_itw); cudaFree(ctx->tw.d_tw2); cudaFree(ctx->tw.d_itw2); cudaFree(ctx->tw.d_ptw2); cudaFree(ctx->tw.d_iptw2);
     ctx->tw = TwiddleBank();
   }
   static bool table_uploaded[64] = {false};
@@ -65,9 +82,15 @@ nb200_status twiddles_prepare(nb200_ctx* ctx, u32 max_domain_log) {
   NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_itw, len * 4));
   NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_tw2, len * 4));
   NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_itw2, len * 4));
+  NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_ptw2, len * 4));
+  NB_CUDA(ctx, cudaMalloc(&ctx->tw.d_iptw2, len * 4));
   ctx->tw.half_log = k;
   u32 threads = 256, blocks = (u32)((len + threads - 1) / threads);
   twiddle_bank_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tw.d_tw, ctx->tw.d_itw, ctx->tw.d_tw2, ctx->tw.d_itw2, k);
+  NB_LAUNCH_CHECK(ctx);
+  twiddle_product_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tw.d_tw, ctx->tw.d_ptw2, k);
+  NB_LAUNCH_CHECK(ctx);
+  twiddle_product_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tw.d_itw, ctx->tw.d_iptw2, k);
   NB_LAUNCH_CHECK(ctx);
   return NB200_OK;
 }

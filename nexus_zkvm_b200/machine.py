@@ -151,7 +151,7 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", r
     ch = backend.channel()
     for byte in associated_data:                      # machine.rs:197-200
         ch.mix_u64(int(byte))
-    log_sizes = [machine.log_size, 8]
+    log_sizes = list(getattr(machine, "log_sizes", None) or [machine.log_size, 8])
     for ls in log_sizes:                              # machine.rs:204-206
         ch.mix_u64(ls)
     prover = backend.prover(machine.words, config)
@@ -162,10 +162,11 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", r
         roots = [prover.commit(machine.preprocessed_columns(), ch, coset_order=True)]
         # tree 1: main trace + extension main columns (machine.rs:230-237)
         main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)  # a 2-D block or a list of columns / blocks
-        roots.append(prover.commit(main_part + [mult], ch, coset_order=True))
+        roots.append(prover.commit(main_part + ([mult] if mult is not None else []), ch, coset_order=True))
     # lookup elements (machine.rs:239-240)
     params = [(0, 0, 0, 0)] * air.n_params
-    machine.range256.draw(ch, params)
+    for rel in (getattr(machine, "relations", None) or [machine.range256]):
+        rel.draw(ch, params)
     # interaction trace per component (machine.rs:242-260); claimed sums mixed before the commit (machine.rs:262-263)
     inter, claimed = [], []
     for k, comp in enumerate(air.components):
@@ -180,6 +181,111 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", r
            "associated_data": bytes(associated_data)}
     proof = prover.prove(ch, params)
     return proof, claimed, aux
+
+
+class MultiMachine:
+    """A prover2-shaped machine: MANY components of DISTINCT log sizes instead of one wide component — the
+    reference's prover2 builds one component per opcode family, each with its own log size (/root/reference
+    prover2/machine/src/lib.rs:9-65) — with constraint degree bounds 1 and 2 mixed (`log_expand`), LogUp fractions batched in
+    pairs where the degree bound allows (prover2/machine/src/lookups/logup_trace_builder.rs:88-101), two shared lookup relations
+    and two table components with preprocessed columns addressed by id:
+      * `Range256` (arity 1) against a 2^8-row table, like prover/src/extensions/multiplicity.rs;
+      * `BitOp` (arity 3: a, b, a XOR b) against a 2^16-row preprocessed table — the shape of the v1 bit-op extension
+        (prover/src/extensions/bit_op.rs) and of the keccak extension's XorTable / BitNotAndTable / BitRotateTable
+        (prover/src/extensions/keccak/mod.rs:12-33: tuple lookups into preprocessed truth tables).
+    Component kinds alternate: `add` (byte-limb ADD with carries, range-checked through Range256; degree 2, fractions one per
+    column) and `xor` (a XOR b = c proven by a BitOp lookup per byte, Range256 on nothing; degree bound 3, fractions in pairs).
+    Every tree therefore holds columns of len(log_sizes) + 2 different sizes, and FRI's first layer has as many column sizes."""
+
+    def __init__(self, log_sizes, lanes=1):
+        assert all(4 <= ls <= 24 for ls in log_sizes)
+        self.comp_log_sizes, self.lanes = list(log_sizes), lanes
+        air = A.Air()
+        self.range256 = air.relation("Range256", 1)
+        self.bitop = air.relation("BitOp", 3)
+        self.relations = [self.range256, self.bitop]
+        self.kinds = []
+        for i, ls in enumerate(log_sizes):
+            kind = "add" if i % 2 == 0 else "xor"
+            self.kinds.append(kind)
+            c = air.component(ls, 1 if kind == "add" else 2)
+            for _ in range(lanes):
+                a = [c.next_trace_mask() for _ in range(4)]
+                b = [c.next_trace_mask() for _ in range(4)]
+                r = [c.next_trace_mask() for _ in range(4)]
+                if kind == "add":
+                    carry = [c.next_trace_mask() for _ in range(4)]
+                    for k in range(4):
+                        c.add_constraint(carry[k] * (1 - carry[k]))
+                        prev = carry[k - 1] if k else 0
+                        c.add_constraint(a[k] + b[k] + prev - r[k] - carry[k] * 256)
+                    for x in a + b + r:
+                        c.add_to_relation(self.range256, 1, [x])
+                else:
+                    for k in range(4):
+                        c.add_to_relation(self.bitop, 1, [a[k], b[k], r[k]])
+            if kind == "add":
+                c.finalize_logup()
+            else:
+                c.finalize_logup_in_pairs()
+        t8 = air.component(8, 1)
+        v8 = t8.get_preprocessed_column("Range256Values")
+        m8 = t8.next_trace_mask()
+        t8.add_to_relation(self.range256, -m8, [v8])
+        t8.finalize_logup()
+        t16 = air.component(16, 1)
+        ta, tb, tc = (t16.get_preprocessed_column(n) for n in ("BitOpA", "BitOpB", "BitOpXor"))
+        m16 = t16.next_trace_mask()
+        t16.add_to_relation(self.bitop, -m16, [ta, tb, tc])
+        t16.finalize_logup()
+        self.air = air
+        self.log_sizes = list(log_sizes) + [8, 16]
+        self.log_size = max(self.log_sizes)
+        self.words = air.serialize()
+
+    def preprocessed_columns(self):
+        cols = [None] * self.air.n_columns()[0]
+        i = np.arange(1 << 16, dtype=np.uint32)
+        cols[self.air.preprocessed_ids["Range256Values"]] = np.arange(256, dtype=np.uint32)
+        cols[self.air.preprocessed_ids["BitOpA"]] = i >> 8
+        cols[self.air.preprocessed_ids["BitOpB"]] = i & 0xFF
+        cols[self.air.preprocessed_ids["BitOpXor"]] = (i >> 8) ^ (i & 0xFF)
+        return cols
+
+    def fill_main_trace(self, seed=0):
+        """Returns the list of main-trace columns in commitment order (component by component, the two multiplicity columns last)."""
+        rng = np.random.default_rng(seed)
+        cols = []
+        h8, h16 = np.zeros(256, np.int64), np.zeros(1 << 16, np.int64)
+        for ls, kind in zip(self.comp_log_sizes, self.kinds):
+            n = 1 << ls
+            for _ in range(self.lanes):
+                a = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+                b = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+                al = [((a >> (8 * k)) & 0xFF).astype(np.uint32) for k in range(4)]
+                bl = [((b >> (8 * k)) & 0xFF).astype(np.uint32) for k in range(4)]
+                if kind == "add":
+                    c = (a + b) & 0xFFFFFFFF
+                    cl = [((c >> (8 * k)) & 0xFF).astype(np.uint32) for k in range(4)]
+                    carry, prev = [], np.zeros(n, np.uint32)
+                    for k in range(4):
+                        prev = ((al[k] + bl[k] + prev) >> 8).astype(np.uint32)
+                        carry.append(prev)
+                    cols += al + bl + cl + carry
+                    for x in al + bl + cl:
+                        h8 += np.bincount(x, minlength=256)
+                else:
+                    cl = [al[k] ^ bl[k] for k in range(4)]
+                    cols += al + bl + cl
+                    for k in range(4):
+                        h16 += np.bincount((al[k] << 8) | bl[k], minlength=1 << 16)
+        cols.append((h8 % P).astype(np.uint32))
+        cols.append((h16 % P).astype(np.uint32))
+        assert len(cols) == self.air.n_columns()[1]
+        return cols
+
+    def column_log_sizes(self):
+        return self.air.column_log_sizes()
 
 
 def verify_claimed_sums(claimed):
