@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py — the hot path's headline measurement: RISC-V cycles PROVED per second at 2^20 rows (BASELINE.json `metric`).
 
-One "step" = ONE WHOLE PROOF of the Nexus-shaped synthetic machine (nexus_zkvm_b200/machine.py, 21 ADD lanes: 3 / 339 / 1012
-committed columns + 4 composition columns — the reference's 27 / 347 / 1012) at 2^log_rows rows, i.e. everything
+One "step" = ONE WHOLE PROOF of the reference's v1 main component as recorded data (nexus_zkvm_b200/nexus_v1.py: the real 27 / 347 /
+1012-column layout, 413 constraints of 13 transcribed chips, all 253 LogUp fractions, two multiplicity tables; padding-only witness —
+`--machine add21` selects round 1's synthetic ADD machine instead) at 2^log_rows rows, i.e. everything
 /root/reference prover/src/machine.rs:186-290 hands to Stwo: three tree commits (Circle iFFT, LDE, Blake2s Merkle), the LogUp
 interaction trace, constraint quotients, the composition commit, OODS evaluation, DEEP quotients, FRI, proof of work, query
 decommitments and the postcard proof bytes.  Host-side trace FILLING is outside the step (the north star keeps it on the CPU).
@@ -46,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--lanes", type=int, default=21)
+    ap.add_argument("--machine", default="nexus_v1", choices=["nexus_v1", "add21"],
+                    help="nexus_v1: the reference's v1 main component as recorded data (nexus_zkvm_b200/nexus_v1.py: 27/347/1012 columns, 413 constraints); "
+                         "add21: the round-1 synthetic ADD machine (3/339/1012 columns, 424 constraints)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-log-rows", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,14 +165,24 @@ def workload_config(args, m, world):
     nc = m.air.n_columns()
     return {"workload": f"full STARK proof (stwo::prover::prove + the 3 trace-tree commits + LogUp interaction trace) of a 2^{args.log_rows}-row synthetic "
                         f"trace, {nc[0]}+{nc[1]}+{nc[2]} M31 columns, blow-up {1 << CONFIG['log_blowup']}, Blake2s Merkle, per GPU",
-            "log_rows": args.log_rows, "columns": int(sum(nc)), "constraints": int(sum(len(c.constraints) for c in m.air.components)),
+            "log_rows": args.log_rows, "columns": int(sum(nc)), "constraints": int(sum(len(c.constraints) for c in m.air.components)), "machine": args.machine,
             "pcs_config": CONFIG, "l2": "working set (tens of GB per proof) far larger than L2; no flush needed",
             "sharding": "one trace segment per GPU (weak scaling) + NCCL all-gather of the Merkle roots" if world > 1 else "single GPU"}
 
 
 def make_machine(args, log_rows=None):
     from nexus_zkvm_b200 import machine as M
+    if args.machine == "nexus_v1":
+        from nexus_zkvm_b200.nexus_v1 import NexusV1Machine
+        return NexusV1Machine(log_rows or args.log_rows)
     return M.AddMachine(log_size=log_rows or args.log_rows, n_lanes=args.lanes)
+
+
+def fill_trace(m, seed):
+    """(main_cols, mult) as nexus_zkvm_b200.machine.prove takes them (plain host arrays; the CPU arm and the verifier use these)."""
+    if hasattr(m, "n_main"):           # NexusV1Machine: a list of all tree-1 columns (multiplicities included)
+        return m.fill_main_trace(seed=seed), None
+    return m.fill_main_trace(seed=seed)
 
 
 def oracle_full_prove(m, cols, mult):
@@ -189,7 +203,7 @@ def run_reference(args):
     from oracle import pyoracle as orc
     orc.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     m = make_machine(args)
-    cols, mult = m.fill_main_trace(seed=0)
+    cols, mult = fill_trace(m, 0)
     t, proof, _aux = oracle_full_prove(m, cols, mult)   # ONE step: a 2^20-row CPU proof takes minutes
     value = (1 << args.log_rows) / t
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
@@ -243,21 +257,38 @@ def main():
     n_rows = 1 << args.log_rows
     m = make_machine(args)
     be = CudaBackend(ctx)
-    # ---- the filled trace, in pinned host memory, packed: `pc` as u32, every other main column (byte limbs, flags) as u8
-    pc_block = ctx.host_alloc(1, args.log_rows)
-    byte_block = ctx.host_alloc_bytes((m.n_main_columns() - 1) << args.log_rows).reshape(m.n_main_columns() - 1, n_rows)
-    host_cols, mult = m.fill_main_trace(seed=rank, packed_out=(pc_block, byte_block))
-    h2d = pc_block.nbytes + byte_block.nbytes + mult.nbytes + sum(c.nbytes for c in m.preprocessed_columns())
+    # ---- the filled trace, in pinned host memory, packed: byte-valued main columns (limbs, flags, register indices) travel as u8
+    if args.machine == "nexus_v1":
+        all_cols, mult = fill_trace(m, rank)
+        byte_block = ctx.host_alloc_bytes(m.n_main << args.log_rows).reshape(m.n_main, n_rows)
+        for i in range(m.n_main):
+            byte_block[i] = all_cols[i]                       # every one of the 347 main columns holds values < 256
+        small = all_cols[m.n_main:]                           # the extension components' multiplicity columns (2^8, 2^5 rows)
+        host_cols = [byte_block] + small
+        wide_blocks = [byte_block]
+        h2d = byte_block.nbytes + sum(c.nbytes for c in small) + sum(c.nbytes for c in m.preprocessed_columns())
+        host_format = "packed: %d u8 columns (widened on the device) + %d small u32 columns" % (m.n_main, len(small))
+        del all_cols
+        pre = m.preprocessed_columns()                        # cached; the big block goes to pinned memory once
+        pinned_pre = ctx.host_alloc_bytes(pre[0].size).reshape(pre[0].shape)
+        pinned_pre[:] = pre[0]
+        m._pre_cache[0] = pinned_pre
+    else:
+        pc_block = ctx.host_alloc(1, args.log_rows)
+        byte_block = ctx.host_alloc_bytes((m.n_main_columns() - 1) << args.log_rows).reshape(m.n_main_columns() - 1, n_rows)
+        host_cols, mult = m.fill_main_trace(seed=rank, packed_out=(pc_block, byte_block))
+        small = [mult]
+        wide_blocks = [pc_block, byte_block]
+        h2d = pc_block.nbytes + byte_block.nbytes + mult.nbytes + sum(c.nbytes for c in m.preprocessed_columns())
+        host_format = "packed: 1 u32 column + %d u8 columns (widened on the device)" % (m.n_main_columns() - 1)
 
     with torch.cuda.stream(stream):
         ctx.precompute_twiddles(args.log_rows + 3)
         # resident copies of trees 0 + 1 (finalized order) for the HBM-resident headline
         up = be.prover(m.words, CONFIG)
         t0_res = up._batches_from_host(m.preprocessed_columns(), True)
-        wide = np.empty((m.n_main_columns(), n_rows), np.uint32)
-        wide[0] = pc_block[0]
-        wide[1:] = byte_block
-        t1_res = [ctx.upload(wide, coset_order=True), ctx.upload(mult[None, :], coset_order=True)]
+        wide = np.concatenate([b.astype(np.uint32) for b in wide_blocks])
+        t1_res = [ctx.upload(wide, coset_order=True)] + [ctx.upload(np.asarray(c, dtype=np.uint32)[None, :], coset_order=True) for c in small]
         del wide, up
         roots_dev = torch.zeros((4, 32), dtype=torch.uint8, device=dev)
         gathered = [torch.zeros_like(roots_dev) for _ in range(world)] if world > 1 else None
@@ -323,7 +354,7 @@ def main():
                 dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             e2e = {"value": world * n_rows / (float(ems.item()) / args.e2e_steps * 1e-3), "unit": UNIT, "ms_per_step": float(ems.item()) / args.e2e_steps,
                    "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": (len(pe) + 4 * 32) * world, "steps": args.e2e_steps,
-                   "host_format": "packed: 1 u32 column + %d u8 columns (widened on the device)" % (m.n_main_columns() - 1)}
+                   "host_format": host_format}
 
         # ---- stage breakdown + roofline of the dominant kernel group (rank 0): CUDA events on the launching stream
         stages, roofline = None, None
@@ -346,7 +377,8 @@ def main():
             for ls in aux["log_sizes"]:
                 ch.mix_u64(ls)
             ch.mix_root(aux["roots"][0]); ch.mix_root(aux["roots"][1])
-            ch.draw_felts(2)
+            for _ in (getattr(m, "relations", None) or [None]):
+                ch.draw_felts(2)                      # LookupElements::draw per relation
             ch.mix_felts(last["claimed"])
             ch.mix_root(aux["roots"][2])
             orc.verify(m.words, np.array(aux["params"], dtype=np.uint32), last["proof"], ch, m.column_log_sizes())
@@ -360,7 +392,7 @@ def main():
             from oracle import pyoracle as orc
             orc.set_num_threads(os.cpu_count() or 1)
             ms_ = make_machine(args, args.cpu_sample_log_rows)
-            cs, mu = ms_.fill_main_trace(seed=0)
+            cs, mu = fill_trace(ms_, 0)
             tcpu, _p, _a = oracle_full_prove(ms_, cs, mu)
             cpu_baseline = {"value": (1 << args.cpu_sample_log_rows) / tcpu, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                             "sample": f"one whole proof of the same machine at 2^{args.cpu_sample_log_rows} rows ({tcpu:.1f} s); `--impl reference` runs the 2^{args.log_rows}-row proof"}
@@ -383,7 +415,7 @@ def strong_commit(args, ctx, torch, dist, dev, stream, rank, world, m, reps=3):
     """One tree (the interaction tree's 2^log_rows-row columns) committed by ALL ranks together: nb200_commit_sharded = column-sharded fused
     iFFT+LDE -> grouped ncclSend/Recv of packed row slices over NVLink -> row-sharded sub-tree hashing -> ncclAllGather of the caps."""
     import nexus_zkvm_b200 as nb
-    total = m.air.n_columns()[2] - 4
+    total = sum(1 for ls in m.column_log_sizes()[2] if ls == args.log_rows)
     ctx.comm_init_from_torch(dist, dev)
     first, count = nb.Context.shard_range(total, world, rank)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
@@ -417,8 +449,7 @@ def commit_breakdown(args, ctx, torch, dev, stream, m):
     peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    nc = m.air.n_columns()
-    big = [nc[0] - 1, nc[1] - 1, nc[2] - 4]     # the 2^log_rows-row columns of each tree (the table component's columns are 2^8 rows)
+    big = [sum(1 for ls in tree if ls == args.log_rows) for tree in m.column_log_sizes()]   # the 2^log_rows-row columns of each trace tree
     n_rows = 1 << args.log_rows
     t_fft = t_mrk = 0.0
     reps = 3

@@ -79,6 +79,8 @@ SHIPPED_MACHINES = [(20, 21, False), (22, 21, False), (16, 21, False), (8, 1, Fa
 
 # prover2-shaped machines (machine.MultiMachine) of tests/test_gpu_prove_parity.py and bench.py --multi: component log sizes
 SHIPPED_MULTI = [list(range(4, 12)), list(range(4, 18)), list(range(4, 22))]
+# the reference's v1 main component as data (nexus_v1.NexusV1Machine): log sizes of the tests, bench.py (16 = CPU sample, 20, 22) and smoke()
+SHIPPED_NEXUS_V1 = [8, 9, 12, 16, 20, 22]
 
 
 def kernel_sources(words):
@@ -116,6 +118,8 @@ def precompile_kernels(machines=SHIPPED_MACHINES, verbose=False):
     todo = {}
     ms = [M.AddMachine(log_size=log_size, n_lanes=lanes, logup_in_pairs=pairs) for log_size, lanes, pairs in machines]
     ms += [M.MultiMachine(sizes) for sizes in SHIPPED_MULTI]
+    from .nexus_v1 import NexusV1Machine
+    ms += [NexusV1Machine(ls) for ls in SHIPPED_NEXUS_V1]
     for m in ms:
         for key, src in kernel_sources(m.words):
             path = os.path.join(JIT_CACHE, f"{key:016x}.cubin")

@@ -79,6 +79,26 @@ def test_multi_component_machine_proof_bytes(backend, sizes):
     verify(m, g_proof, o_aux)
 
 
+@pytest.mark.parametrize("log_size", [9, 12])
+def test_nexus_v1_main_component_proof_bytes(backend, log_size):
+    """The reference's v1 main component recorded as data (nexus_zkvm_b200/nexus_v1.py: 27/347/1012 columns, 413 constraints, 253 LogUp
+    fractions over 9 relations with tuples of 1..9 values, next-row masks on Pc / IsPadding) with its padding-only witness: the GPU's proof
+    bytes equal the oracle's and the oracle's verifier accepts them; an un-padded row is rejected."""
+    from nexus_zkvm_b200.nexus_v1 import NexusV1Machine, MAIN_COLUMNS
+    m = NexusV1Machine(log_size)
+    cols = m.fill_main_trace(seed=log_size)
+    g_proof, g_claimed, g_aux = M.prove(m, backend, cols, None, associated_data=b"v1")
+    o_proof, o_claimed, o_aux = M.prove(m, OracleBackend(), cols, None, associated_data=b"v1")
+    assert g_aux["roots"] == o_aux["roots"]
+    assert g_claimed == o_claimed and M.verify_claimed_sums(g_claimed)
+    assert g_proof == o_proof, f"proof bytes differ (len {len(g_proof)} vs {len(o_proof)})"
+    verify(m, g_proof, o_aux)
+    off = sum(s for n, s in MAIN_COLUMNS[:[n for n, _ in MAIN_COLUMNS].index("IsPadding")])
+    cols[off] = cols[off].copy(); cols[off][5] = 0           # row 5 claims to execute something: the one-hot opcode sum (cpu.rs:379-420) fails
+    with pytest.raises(nb.Nb200Error, match="status 5"):
+        M.prove(m, backend, cols, None)
+
+
 def test_non_default_config(backend):
     m = M.AddMachine(log_size=9, n_lanes=1)
     cols, mult = m.fill_main_trace(seed=77)

@@ -118,3 +118,23 @@ def test_half_domain_decomposition_used_by_the_quotient_step():
         assert len(ts) == 1
         t = ts.pop()
         assert all((int(e_lo[i]) + t * int(e_hi[i])) % P == int(full[i]) for i in range(h))
+
+
+def test_nexus_v1_main_component_oracle_prove_and_verify():
+    """The recorded v1 main component (nexus_zkvm_b200/nexus_v1.py) with its padding-only witness: the oracle proves it, its verifier accepts,
+    the LogUp sums of the three components cancel, the column counts are the reference's 27 / 347 / 1012 (+ the two tables' columns), and a row
+    that is not padding (without a matching opcode flag) is rejected."""
+    from nexus_zkvm_b200 import machine as M
+    from nexus_zkvm_b200.nexus_v1 import NexusV1Machine, MAIN_COLUMNS
+    from tests.oracle_backend import OracleBackend, verify
+    m = NexusV1Machine(8)
+    assert m.air.n_columns() == [27 + 2, 347 + 2, 1012 + 8]
+    assert [len(c.fracs) for c in m.air.components] == [253, 1, 1]
+    cols = m.fill_main_trace(seed=3)
+    proof, claimed, aux = M.prove(m, OracleBackend(), cols, None)
+    assert M.verify_claimed_sums(claimed)
+    verify(m, proof, aux)
+    off = sum(s for n, s in MAIN_COLUMNS[:[n for n, _ in MAIN_COLUMNS].index("IsPadding")])
+    cols[off] = cols[off].copy(); cols[off][7] = 0
+    with pytest.raises(Exception, match="ConstraintsNotSatisfied"):
+        M.prove(m, OracleBackend(), cols, None)
