@@ -112,8 +112,8 @@ class NexusV1Machine:
     multiplicity tables the witness below needs are built (Multiplicity256, Multiplicity32: extensions/multiplicity.rs).
     The witness is a PADDING-ONLY execution (every row IsPadding = 1, the state the reference pads short programs with): all opcode flags are zero, so
     every gated constraint holds and every column the transcribed chips leave free carries random in-range values (bytes, 5-bit register indices);
-    timestamps follow TimestampChip's borrow arithmetic against the preprocessed Reg{1,2,3}TsCur = 3 clk + {1,2,3}.  The oracle proves and verifies
-    it (tests/test_oracle_prove.py, tests/test_gpu_prove_parity.py), so the kernels are measured on the reference's mask layout, constraint
+    timestamps follow TimestampChip's borrow arithmetic against the preprocessed Reg{1,2,3}TsCur = 3 clk + {1,2,3}.  The CPU checker proves and verifies
+    it (tests/), so the kernels are measured on the reference's mask layout, constraint
     shapes (selector x linear combination, degree <= 4) and lookup structure instead of AddMachine's toy AIR."""
 
     def __init__(self, log_size):
