@@ -286,7 +286,12 @@ def main():
         ctx.precompute_twiddles(args.log_rows + 3)
         # resident copies of trees 0 + 1 (finalized order) for the HBM-resident headline
         up = be.prover(m.words, CONFIG)
-        t0_res = up._batches_from_host(m.preprocessed_columns(), True)
+        pre_cols = []
+        for c_ in m.preprocessed_columns():
+            a_ = np.asarray(c_)
+            pre_cols += list(a_.astype(np.uint32)) if a_.ndim == 2 else [a_]
+        t0_res = up._batches_from_host(pre_cols, True)
+        del pre_cols
         wide = np.concatenate([b.astype(np.uint32) for b in wide_blocks])
         t1_res = [ctx.upload(wide, coset_order=True)] + [ctx.upload(np.asarray(c, dtype=np.uint32)[None, :], coset_order=True) for c in small]
         del wide, up

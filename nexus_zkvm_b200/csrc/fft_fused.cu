@@ -381,7 +381,7 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
     const u32* ev = evals + c0 * len;
     u32* co = coeffs + c0 * len;
     // A
-    static const int var_a = env_int("NB200_FFT_VAR_A", 0), var_b = env_int("NB200_FFT_VAR_B", 0), var_c = env_int("NB200_FFT_VAR_C", 0);   // tuning knobs (profiles/README.md)
+    static const int var_a = env_int("NB200_FFT_VAR_A", 0), var_b = env_int("NB200_FFT_VAR_B", 3), var_c = env_int("NB200_FFT_VAR_C", 0);   // tuning knobs (profiles/README.md)
     if (pl.LA == 12) {
       if (var_a == 1) NB_TRY((launch_contig<true, 12, 3, 4>(ctx, st, ev, len, co, len, nc, n, n)));
       else if (var_a == 2) NB_TRY((launch_contig<true, 12, 2, 4>(ctx, st, ev, len, co, len, nc, n, n)));
