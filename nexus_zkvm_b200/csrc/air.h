@@ -81,6 +81,13 @@ inline AirProgram air_parse(const u32* w, size_t n) {
     c.cumsum_shift_param = rd(); c.interaction_col0 = rd();
     air_check_prog(c.prog, c.n_base_regs, c.n_ext_regs, c.masks.size(), a.n_params);
     air_check_prog(c.logup_prog, c.lg_base_regs, c.lg_ext_regs, c.masks.size(), a.n_params);
+    // the interaction-trace generator reads the trace domain row by row: a lookup fraction built from a next-row value or from an interaction
+    // column has no upstream counterpart (LogupTraceGenerator sees only the current row of the original / preprocessed traces) and would silently
+    // read zeros in logup_generate — reject it here instead of failing the proof at the very end
+    for (auto& in : c.logup_prog) {
+      if (in.op == OP_LOADM && (c.masks[in.a].off != 0 || c.masks[in.a].tree == 2)) throw std::runtime_error("air: a logup fraction reads a mask with a row offset or an interaction column");
+      if (in.op == OP_LOADME) throw std::runtime_error("air: a logup fraction reads an extension (interaction) mask");
+    }
     u32 nconstr = 0, nfr = 0;
     for (auto& in : c.prog) if (in.op == OP_CONSTRB || in.op == OP_CONSTRE) ++nconstr;
     for (auto& in : c.logup_prog) if (in.op == OP_FRAC) ++nfr;

@@ -364,7 +364,7 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
 }
 
 // coefficients (4 columns of 2^elog, circle-FFT basis) of the quotient polynomial held by a Q_HALF accumulator pair; lo/hi are consumed
-static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* hi, u32 elog, u32* out /* 4 columns, stride 2^elog */) {
+static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* hi, u32 elog, u32* out /* 4 columns */, size_t out_stride /* >= 2^elog */) {
   const u32 h = elog - 1;
   const size_t hl = (size_t)1 << h;
   NB_TRY(fft_interpolate(ctx, lo->d, lo->d, 4, h));                 // lo = coefficients of q mod pi^(elog-2)
@@ -373,8 +373,10 @@ static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* h
   NB_TRY(fft_evaluate(ctx, lo->d, h, t.c->d, h, 4, elog));          // lo evaluated on D2
   NB_TRY(sub_scale_top_twiddle(ctx, hi->d, t.c->d, 4 * hl, elog));  // (q|D2 - lo|D2) / t
   NB_TRY(fft_interpolate(ctx, hi->d, hi->d, 4, h, elog));           // hi coefficients
-  NB_TRY(add_cols_strided(ctx, out, (size_t)1 << elog, lo->d, hl, hl, 4));
-  NB_TRY(add_cols_strided(ctx, out + hl, (size_t)1 << elog, hi->d, hl, hl, 4));
+  // the composition's coefficient columns are 2^comp_log apart; this accumulator's polynomial may be smaller (a machine whose largest
+  // evaluation domain belongs to another component): found by the prover2-shaped machine, tests/test_gpu_prove_parity.py
+  NB_TRY(add_cols_strided(ctx, out, out_stride, lo->d, hl, hl, 4));
+  NB_TRY(add_cols_strided(ctx, out + hl, out_stride, hi->d, hl, hl, 4));
   return NB200_OK;
 }
 
@@ -468,7 +470,7 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     for (auto& kv : acc) {
       if (st != NB200_OK) break;
       const u32 elog = kv.first.first;
-      if (kv.first.second == Q_HALF) st = half_to_coeffs(ctx, kv.second.a, kv.second.b, elog, cur->d);
+      if (kv.first.second == Q_HALF) st = half_to_coeffs(ctx, kv.second.a, kv.second.b, elog, cur->d, (size_t)1 << comp_log);
       else {
         st = fft_interpolate(ctx, kv.second.a->d, kv.second.a->d, 4, elog);
         if (st == NB200_OK) st = add_cols_strided(ctx, cur->d, (size_t)1 << comp_log, kv.second.a->d, (size_t)1 << elog, (size_t)1 << elog, 4);

@@ -46,6 +46,13 @@ class CudaEngine:
     def __init__(self, ctx, merkle_hash=0):
         self.ctx, self.merkle_hash = ctx, merkle_hash
 
+    def _fence(self):
+        """The ctx may run on its own non-blocking stream, which has no implicit ordering with torch's current stream: drain both sides around
+        every ABI call that touches torch tensors (this path is the older torch-collective variant; nb200_commit_sharded needs none of this)."""
+        import torch
+        torch.cuda.current_stream().synchronize()
+        self.ctx.sync()
+
     def lde(self, evals, log_blowup):
         """evals: (n_cols, 2^log) int32 device tensor -> (n_cols, 2^(log+blowup)) int32 device tensor."""
         import torch
@@ -60,6 +67,7 @@ class CudaEngine:
         cob = self.ctx.wrap_device(co.data_ptr(), n_cols, log)
         ldb = self.ctx.wrap_device(out.data_ptr(), n_cols, log + log_blowup)
         co.copy_(evals)
+        self._fence()
         self.ctx.interpolate(cob)
         self.ctx._chk(lib().nb200_evaluate(self.ctx._h, cob._h, C.c_uint32(log_blowup), ldb._h))
         self.ctx.sync()
@@ -69,6 +77,7 @@ class CudaEngine:
     def subtree_root(self, cols):
         """cols: (n_cols, rows) int32 device tensor -> 32-byte root of the Merkle tree over these rows."""
         n_cols, rows = cols.shape
+        self._fence()   # `cols` comes out of a torch collective on torch's stream
         b = self.ctx.wrap_device(cols.data_ptr(), n_cols, rows.bit_length() - 1)
         return self.ctx.merkle_commit([b]).root
 
