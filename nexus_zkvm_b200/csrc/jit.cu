@@ -137,6 +137,60 @@ void emit_op(std::ostringstream& o, const AirInstr& in, Ld ld) {
   }
 }
 
+// Which virtual registers cross a chunk boundary?  live_in[ci] = registers read in chunk ci or later before they are rewritten.  A chunk loads only
+// those from the state struct and stores only the ones it wrote that a later chunk still reads: the real v1 AIR keeps 26 base + 15 secure
+// registers alive somewhere (shared selectors such as IsTypeR), and copying all 90 words in and out of local memory at each of its 19 chunk
+// boundaries cost more than the arithmetic (the synthetic ADD machine has 4 + 4 and never showed it).
+struct ChunkLive { std::vector<std::vector<u32>> in_b, in_e, out_b, out_e; };
+static void instr_regs(const AirInstr& in, std::vector<u32>& rb, std::vector<u32>& re, int& wb, int& we) {
+  wb = we = -1;
+  switch (in.op) {
+    case OP_LOADM: case OP_CONSTB: wb = (int)in.dst; break;
+    case OP_ADDB: case OP_SUBB: case OP_MULB: rb = {in.a, in.b}; wb = (int)in.dst; break;
+    case OP_NEGB: rb = {in.a}; wb = (int)in.dst; break;
+    case OP_PARAME: case OP_LOADME: we = (int)in.dst; break;
+    case OP_ADDE: case OP_SUBE: case OP_MULE: re = {in.a, in.b}; we = (int)in.dst; break;
+    case OP_NEGE: re = {in.a}; we = (int)in.dst; break;
+    case OP_ADDEB: case OP_SUBEB: case OP_MULEB: re = {in.a}; rb = {in.b}; we = (int)in.dst; break;
+    case OP_BTOE: rb = {in.a}; we = (int)in.dst; break;
+    case OP_CONSTRB: rb = {in.a}; break;
+    case OP_CONSTRE: re = {in.a}; break;
+    case OP_FRAC: re = {in.a, in.b}; break;
+    default: break;
+  }
+}
+static ChunkLive chunk_liveness(const std::vector<AirInstr>& prog, size_t CH, u32 nb, u32 ne) {
+  const size_t n_chunks = (prog.size() + CH - 1) / CH;
+  ChunkLive L; L.in_b.resize(n_chunks); L.in_e.resize(n_chunks); L.out_b.resize(n_chunks); L.out_e.resize(n_chunks);
+  std::vector<char> lb(nb + 1, 0), le(ne + 1, 0);
+  std::vector<std::vector<char>> after_b(n_chunks), after_e(n_chunks);   // live sets at the END of each chunk
+  for (size_t ci = n_chunks; ci-- > 0;) {
+    after_b[ci] = lb; after_e[ci] = le;
+    for (size_t pc = std::min(prog.size(), (ci + 1) * CH); pc-- > ci * CH;) {
+      std::vector<u32> rb, re; int wb, we;
+      instr_regs(prog[pc], rb, re, wb, we);
+      if (wb >= 0) lb[wb] = 0;
+      if (we >= 0) le[we] = 0;
+      for (u32 r : rb) lb[r] = 1;
+      for (u32 r : re) le[r] = 1;
+    }
+    for (u32 r = 0; r < nb; ++r) if (lb[r]) L.in_b[ci].push_back(r);
+    for (u32 r = 0; r < ne; ++r) if (le[r]) L.in_e[ci].push_back(r);
+  }
+  for (size_t ci = 0; ci < n_chunks; ++ci) {
+    std::vector<char> wrb(nb + 1, 0), wre(ne + 1, 0);
+    for (size_t pc = ci * CH; pc < std::min(prog.size(), (ci + 1) * CH); ++pc) {
+      std::vector<u32> rb, re; int wb, we;
+      instr_regs(prog[pc], rb, re, wb, we);
+      if (wb >= 0) wrb[wb] = 1;
+      if (we >= 0) wre[we] = 1;
+    }
+    for (u32 r = 0; r < nb; ++r) if (wrb[r] && after_b[ci][r]) L.out_b[ci].push_back(r);
+    for (u32 r = 0; r < ne; ++r) if (wre[r] && after_e[ci][r]) L.out_e[ci].push_back(r);
+  }
+  return L;
+}
+
 std::string gen_source(const AirComponent& c) {
   std::ostringstream o;
   o << kPrelude;
@@ -158,11 +212,14 @@ std::string gen_source(const AirComponent& c) {
   size_t CH = 250;
   if (const char* e = getenv("NB200_JIT_CHUNK")) { long v = atol(e); if (v >= 16 && v <= 100000) CH = (size_t)v; }
   size_t n_chunks = (c.prog.size() + CH - 1) / CH;
+  const ChunkLive live = chunk_liveness(c.prog, CH, nb, ne);
   u32 k = 0;
   for (size_t ci = 0; ci < n_chunks; ++ci) {
     o << "__device__ __noinline__ void chunk" << ci << "(St& s, const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff, u32 row, u32 EL) {\n";
     o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q rr = s.rr;\n";
-    o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
+    for (u32 r : live.in_b[ci]) o << "  b[" << r << "] = s.b[" << r << "];";
+    for (u32 r : live.in_e[ci]) o << "  e[" << r << "] = s.e[" << r << "];";
+    o << "\n";
     for (size_t pc = ci * CH; pc < std::min(c.prog.size(), (ci + 1) * CH); ++pc) {
       const AirInstr& in = c.prog[pc];
       o << "  ";
@@ -173,7 +230,9 @@ std::string gen_source(const AirComponent& c) {
       }
       o << "\n";
     }
-    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.rr = rr;\n}\n";
+    for (u32 r : live.out_b[ci]) o << "  s.b[" << r << "] = b[" << r << "];";
+    for (u32 r : live.out_e[ci]) o << "  s.e[" << r << "] = e[" << r << "];";
+    o << "\n  s.rr = rr;\n}\n";
   }
   // The CTAs re-converge (__syncthreads) after every chunk: the warps of a CTA then execute the same few tens of KB of straight-line
   // code at a time and the instruction cache serves them from one fetch.  Without the barriers the warps drift apart over the ~0.7 MB
@@ -206,6 +265,7 @@ std::string gen_logup_source(const AirComponent& c) {
   };
   size_t CH = 150;
   size_t n_chunks = (c.logup_prog.size() + CH - 1) / CH;
+  const ChunkLive live = chunk_liveness(c.logup_prog, CH, nb, ne);
   // The QM31 inverse (one per batch of fractions; 38 M31 products for x^(P-2) alone) is batched over G consecutive batches of the same
   // row: prefix products, ONE inverse, back-substitution (3 products per extra batch).  The inverse is unique, so the values are the
   // interpreter's.  `pending` batches wait in pfn/pfd until the group is full; the running row sum is then advanced batch by batch.
@@ -238,7 +298,9 @@ std::string gen_logup_source(const AirComponent& c) {
     o << "__device__ __noinline__ void chunk" << ci << "(St& s, Pend& pe, const u32* const* __restrict__ cols, const u32* __restrict__ params, u32* __restrict__ out, u32 row, u32 LS) {\n";
     o << "  u32 b[" << nb << "]; Q e[" << ne << "]; Q fn = s.fn, fd = s.fd, run = s.run;\n";
     for (int g = 0; g < G; ++g) o << "  Q pfn" << g << " = pe.n[" << g << "], pfd" << g << " = pe.d[" << g << "];\n";
-    o << "  for (int i = 0; i < " << nb << "; ++i) b[i] = s.b[i];\n  for (int i = 0; i < " << ne << "; ++i) e[i] = s.e[i];\n";
+    for (u32 r : live.in_b[ci]) o << "  b[" << r << "] = s.b[" << r << "];";
+    for (u32 r : live.in_e[ci]) o << "  e[" << r << "] = s.e[" << r << "];";
+    o << "\n";
     for (size_t pc = ci * CH; pc < std::min(c.logup_prog.size(), (ci + 1) * CH); ++pc) {
       const AirInstr& in = c.logup_prog[pc];
       if (in.op == OP_FRAC) {
@@ -252,7 +314,9 @@ std::string gen_logup_source(const AirComponent& c) {
       }
     }
     if (ci + 1 == n_chunks) { if (have) finalize(o); flush(o); }
-    o << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = b[i];\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = e[i];\n  s.fn = fn; s.fd = fd; s.run = run;\n";
+    for (u32 r : live.out_b[ci]) o << "  s.b[" << r << "] = b[" << r << "];";
+    for (u32 r : live.out_e[ci]) o << "  s.e[" << r << "] = e[" << r << "];";
+    o << "\n  s.fn = fn; s.fd = fd; s.run = run;\n";
     for (int g = 0; g < G; ++g) o << "  pe.n[" << g << "] = pfn" << g << "; pe.d[" << g << "] = pfd" << g << ";\n";
     o << "}\n";
   }
@@ -298,7 +362,7 @@ uint64_t jit_source_key(const std::string& src) {
   uint64_t h = 1469598103934665603ull;
   auto mix = [&](const char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } };
   mix(src.data(), src.size());
-  const char* tgt = "|sm_100a|nb200-jit-1";
+  const char* tgt = "|sm_100a|nb200-jit-2";
   mix(tgt, strlen(tgt));
   return h;
 }

@@ -86,20 +86,45 @@ def coeff_table(coeffs):
     return t
 
 
-@pytest.mark.parametrize("lanes,pairs", [(1, False), (2, True)])
-def test_generated_constraint_kernel_matches_the_oracle_on_the_cpu(tmp_path, lanes, pairs):
+def _machine(kind, seed):
+    """(machine, tree-1 host columns): the synthetic ADD machine, or the recorded v1 main component (19 code chunks, 26 + 15 live virtual
+    registers: the case the chunk-boundary liveness analysis of csrc/jit.cu exists for)."""
+    if kind == "nexus_v1":
+        from nexus_zkvm_b200.nexus_v1 import NexusV1Machine
+        m = NexusV1Machine(8)
+        return m, m.fill_main_trace(seed=seed)
+    lanes, pairs = kind
     m = M.AddMachine(log_size=8, n_lanes=lanes, logup_in_pairs=pairs)
-    cols, mult = m.fill_main_trace(seed=9 + lanes, n_padding=2)
+    cols, mult = m.fill_main_trace(seed=seed + lanes, n_padding=2)
+    return m, list(cols) + [mult]
+
+
+def _flat(cols):
+    out = []
+    for c in cols:
+        a = np.asarray(c)
+        out += list(a.astype(np.uint32)) if a.ndim == 2 else [np.ascontiguousarray(a, dtype=np.uint32)]
+    return out
+
+
+def _draw(m, ch, params):
+    for rel in (getattr(m, "relations", None) or [m.range256]):
+        rel.draw(ch, params)
+
+
+@pytest.mark.parametrize("kind", [(1, False), (2, True), "nexus_v1"])
+def test_generated_constraint_kernel_matches_the_oracle_on_the_cpu(tmp_path, kind):
+    m, t1 = _machine(kind, 9)
     # the oracle side: commit the three trees exactly as Machine::prove does
     be = OracleBackend()
     ch = be.channel()
     p = be.prover(m.words, dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3))
-    tree0 = [orc.finalize_column(np.ascontiguousarray(c, dtype=np.uint32)) for c in m.preprocessed_columns()]
-    tree1 = [orc.finalize_column(np.ascontiguousarray(c, dtype=np.uint32)) for c in list(cols) + [mult]]
+    tree0 = [orc.finalize_column(c) for c in _flat(m.preprocessed_columns())]
+    tree1 = [orc.finalize_column(c) for c in _flat(t1)]
     p.commit(m.preprocessed_columns(), ch, coset_order=True)
-    p.commit(list(cols) + [mult], ch, coset_order=True)
+    p.commit(t1, ch, coset_order=True)
     params = [(0, 0, 0, 0)] * m.air.n_params
-    m.range256.draw(ch, params)
+    _draw(m, ch, params)
     inter = []
     for k, comp in enumerate(m.air.components):
         c, cs = p.gen_interaction(k, comp.log_size, max(comp.batching) + 1, params)
@@ -159,21 +184,20 @@ extern "C" void run_rows(const unsigned* const* cols, const unsigned* params, un
 '''
 
 
-@pytest.mark.parametrize("lanes,pairs", [(1, False), (2, True)])
-def test_generated_logup_kernel_matches_the_oracle_on_the_cpu(tmp_path, lanes, pairs):
+@pytest.mark.parametrize("kind", [(1, False), (2, True), "nexus_v1"])
+def test_generated_logup_kernel_matches_the_oracle_on_the_cpu(tmp_path, kind):
     """The generated interaction-trace kernel (batched QM31 inverses, running row sums): every logup column except the last secure
     column (which additionally gets the coset-order prefix sum outside the kernel) must equal the oracle's LogupTraceGenerator."""
-    m = M.AddMachine(log_size=8, n_lanes=lanes, logup_in_pairs=pairs)
-    cols, mult = m.fill_main_trace(seed=4 + lanes, n_padding=1)
+    m, t1 = _machine(kind, 4)
     be = OracleBackend()
     ch = be.channel()
     p = be.prover(m.words, dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3))
-    tree0 = [orc.finalize_column(np.ascontiguousarray(c, dtype=np.uint32)) for c in m.preprocessed_columns()]
-    tree1 = [orc.finalize_column(np.ascontiguousarray(c, dtype=np.uint32)) for c in list(cols) + [mult]]
+    tree0 = [orc.finalize_column(c) for c in _flat(m.preprocessed_columns())]
+    tree1 = [orc.finalize_column(c) for c in _flat(t1)]
     p.commit(m.preprocessed_columns(), ch, coset_order=True)
-    p.commit(list(cols) + [mult], ch, coset_order=True)
+    p.commit(t1, ch, coset_order=True)
     params = [(0, 0, 0, 0)] * m.air.n_params
-    m.range256.draw(ch, params)
+    _draw(m, ch, params)
     comp = m.air.components[0]
     n_logup = max(comp.batching) + 1
     want, _cs = p.gen_interaction(0, comp.log_size, n_logup, params)
