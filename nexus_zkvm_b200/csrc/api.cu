@@ -41,7 +41,7 @@ nb200_status nb200_ctx_create(int device, nb200_ctx** out) {
   nb200_ctx* ctx = new nb200_ctx();
   ctx->device = device;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { ctx->sm_count = prop.multiProcessorCount; ctx->total_mem = prop.totalGlobalMem; }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { global_err() = cudaGetErrorString(e); delete ctx; return NB200_ERR_CUDA; }
   ctx->own_stream = true;
@@ -114,6 +114,7 @@ nb200_status nb200_cols_alloc(nb200_ctx* ctx, size_t n_cols, uint32_t log_size, 
   if (bytes) {
     cudaError_t e = dmalloc(ctx, (void**)&c->d, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); delete c; return set_err(ctx, NB200_ERR_OOM, std::string("cols_alloc: ") + cudaGetErrorString(e)); }
+    ctx->live_bytes += bytes;
   }
   *out = c;
   return NB200_OK;
@@ -128,7 +129,11 @@ nb200_status nb200_cols_from_device(nb200_ctx* ctx, void* device_ptr, size_t n_c
 }
 void nb200_cols_free(nb200_ctx*, nb200_cols* c) {
   if (!c) return;
-  if (c->owns && c->d) dfree(c->ctx, c->d);
+  if (c->owns && c->d) {
+    dfree(c->ctx, c->d);
+    const size_t bytes = (c->n_cols << c->log_size) * 4;
+    c->ctx->live_bytes = c->ctx->live_bytes >= bytes ? c->ctx->live_bytes - bytes : 0;
+  }
   delete c;
 }
 size_t nb200_cols_count(const nb200_cols* c) { return c ? c->n_cols : 0; }

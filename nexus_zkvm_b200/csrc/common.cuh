@@ -44,6 +44,9 @@ struct nb200_ctx {
   cudaStream_t chunk_stream[2] = {nullptr, nullptr};
   cudaEvent_t chunk_ev[3] = {nullptr, nullptr, nullptr};
   void* comm = nullptr;                // NCCL communicator state (comm.cu), nullptr = single GPU
+  size_t total_mem = 0;                // device memory (bytes), read once at ctx creation
+  size_t live_bytes = 0;               // bytes held by nb200_cols batches of this ctx (the dominant allocations): the library's own accounting —
+                                       // cudaMemGetInfo stalls for milliseconds while stream-ordered frees are pending and does not see the pool
 };
 #define NB_MAX_DEVICES 64
 

@@ -100,9 +100,8 @@ nb200_status scheme_commit_evals(nb200_scheme* s, const nb200_cols* const* evals
     nb200_cols* hx = nullptr;
     const u32 lde_log = lde->log_size;
     if (s->hint_log_expand == s->log_blowup + 1 && lde_log > 8) {
-      size_t free_b = 0, total_b = 0;
       const size_t need = (co->n_cols << lde_log) * 4;
-      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > need + ((size_t)24 << 30) && twiddles_prepare(ctx, lde_log + 1) == NB200_OK)
+      if (ctx->live_bytes + need + ((size_t)40 << 30) < ctx->total_mem && twiddles_prepare(ctx, lde_log + 1) == NB200_OK)
         if (nb200_cols_alloc(ctx, co->n_cols, lde_log, &hx) != NB200_OK) hx = nullptr;
     }
     t.half_ext.push_back(hx);
