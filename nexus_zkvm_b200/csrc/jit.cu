@@ -203,10 +203,13 @@ std::string gen_source(const AirComponent& c) {
     << "  return __brev((u32)v) >> (32 - EL); }\n";
   const u32 nb = c.n_base_regs ? c.n_base_regs : 1, ne = c.n_ext_regs ? c.n_ext_regs : 1;
   o << "struct St { u32 b[" << nb << "]; Q e[" << ne << "]; Q rr; };\n";
+  // column base pointers live in constant memory (filled before every launch): an access costs no pointer load from global memory
+  // (the real AIR reads 2765 mask values per row: one dependent global load less per value)
+  o << "#define NB_NMASKS " << c.masks.size() << "\n__constant__ const u32* ccols[NB_NMASKS > 0 ? NB_NMASKS : 1];\n";
   auto ld = [&](u32 m) {
     std::ostringstream s;
-    if (c.masks[m].off == 0) s << "__ldg(cols[" << m << "] + row)";
-    else s << "__ldg(cols[" << m << "] + offrow(row, " << c.masks[m].off << ", EL))";
+    if (c.masks[m].off == 0) s << "__ldg(ccols[" << m << "] + row)";
+    else s << "__ldg(ccols[" << m << "] + offrow(row, " << c.masks[m].off << ", EL))";
     return s.str();
   };
   size_t CH = 250;
@@ -256,10 +259,11 @@ std::string gen_logup_source(const AirComponent& c) {
   o << kPrelude;
   const u32 nb = c.lg_base_regs ? c.lg_base_regs : 1, ne = c.lg_ext_regs ? c.lg_ext_regs : 1;
   o << "struct St { u32 b[" << nb << "]; Q e[" << ne << "]; Q fn, fd, run; };\n";
+  o << "#define NB_NMASKS " << c.masks.size() << "\n__constant__ const u32* ccols[NB_NMASKS > 0 ? NB_NMASKS : 1];\n";
   auto ld = [&](u32 m) {
     std::ostringstream s;
     // next-row masks and interaction-trace masks are not inputs of the logup program (they read as zero, as in the interpreter)
-    if (m < c.masks.size() && c.masks[m].off == 0 && c.masks[m].tree != 2) s << "__ldg(cols[" << m << "] + row)";
+    if (m < c.masks.size() && c.masks[m].off == 0 && c.masks[m].tree != 2) s << "__ldg(ccols[" << m << "] + row)";
     else s << "0u";
     return s.str();
   };
@@ -362,7 +366,7 @@ uint64_t jit_source_key(const std::string& src) {
   uint64_t h = 1469598103934665603ull;
   auto mix = [&](const char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } };
   mix(src.data(), src.size());
-  const char* tgt = "|sm_100a|nb200-jit-2";
+  const char* tgt = "|sm_100a|nb200-jit-3";
   mix(tgt, strlen(tgt));
   return h;
 }
@@ -450,9 +454,20 @@ void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out) {
   }
 }
 
+// the kernel's column pointers: device array -> the module's __constant__ table, in stream order
+static nb200_status jit_set_cols(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols) {
+  void* dptr = nullptr; size_t bytes = 0;
+  cudaError_t e = cudaLibraryGetGlobal(&dptr, &bytes, (cudaLibrary_t)jk.lib, "ccols");
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit: cudaLibraryGetGlobal(ccols): ") + cudaGetErrorString(e));
+  e = cudaMemcpyAsync(dptr, d_cols, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit: ccols copy: ") + cudaGetErrorString(e));
+  return NB200_OK;
+}
+
 nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, u32* d_out, u32 log_size) {
   size_t rows = (size_t)1 << log_size;
   if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
+  NB_TRY(jit_set_cols(ctx, jk, d_cols));
   void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_out, (void*)&log_size};
   cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / jit_block())), dim3(jit_block()), args, 0, ctx->stream);
   ctx->launches += 1;
@@ -464,6 +479,7 @@ nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u
                                     u32 rows_log, u32 dom_log) {
   size_t rows = (size_t)1 << rows_log;
   if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
+  NB_TRY(jit_set_cols(ctx, jk, d_cols));
   u32 el = dom_log;
   u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
   void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3, (void*)&el};

@@ -27,6 +27,7 @@ struct uint2 { unsigned x, y; };
 #define __global__
 #define __restrict__
 #define __launch_bounds__(...)
+#define __constant__
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (s & 31)); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i); return r; }
@@ -39,6 +40,7 @@ DRIVER = r'''
 extern "C" void run_rows(const unsigned* const* cols, const unsigned* params, const unsigned* coeff, const unsigned* dinv,
                          unsigned* a0, unsigned* a1, unsigned* a2, unsigned* a3, unsigned EL, unsigned rows) {
   blockDim.x = 1; threadIdx.x = 0;
+  for (unsigned i = 0; i < NB_NMASKS; ++i) ccols[i] = cols[i];   // the library fills the __constant__ table before each launch
   for (unsigned r = 0; r < rows; ++r) { blockIdx.x = r; nbjit(cols, params, coeff, dinv, a0, a1, a2, a3, EL); }
 }
 '''
@@ -179,6 +181,7 @@ def test_generated_constraint_kernel_matches_the_oracle_on_the_cpu(tmp_path, kin
 LOGUP_DRIVER = r'''
 extern "C" void run_rows(const unsigned* const* cols, const unsigned* params, unsigned* out, unsigned LS, unsigned rows) {
   blockDim.x = 1; threadIdx.x = 0;
+  for (unsigned i = 0; i < NB_NMASKS; ++i) ccols[i] = cols[i];
   for (unsigned r = 0; r < rows; ++r) { blockIdx.x = r; nbjit(cols, params, out, LS); }
 }
 '''
