@@ -41,6 +41,23 @@ __global__ void __launch_bounds__(EP_THREADS) eval_points_partial_kernel(const u
     // raw 64-bit products: four of them (< 2^62 each) plus a reduced carry-in fit, so reduce after every fourth term; the four
     // coefficient loads of a group are issued together
     u32 j = 0;
+    // eight coefficient loads (two reduction groups) are in flight per thread before any arithmetic: the sweep is latency bound otherwise
+    for (; j + 8 <= nj; j += 8) {
+      u32 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(c + ((size_t)(j + u) << LB) + t);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 w0 = *reinterpret_cast<const uint4*>(wmid + 4 * (j + 4 * h)), w1 = *reinterpret_cast<const uint4*>(wmid + 4 * (j + 4 * h) + 4);
+        const uint4 w2 = *reinterpret_cast<const uint4*>(wmid + 4 * (j + 4 * h) + 8), w3 = *reinterpret_cast<const uint4*>(wmid + 4 * (j + 4 * h) + 12);
+        const u32 v0 = v[4 * h], v1 = v[4 * h + 1], v2 = v[4 * h + 2], v3 = v[4 * h + 3];
+        a0 += (u64)v0 * w0.x + (u64)v1 * w1.x + (u64)v2 * w2.x + (u64)v3 * w3.x;
+        a1 += (u64)v0 * w0.y + (u64)v1 * w1.y + (u64)v2 * w2.y + (u64)v3 * w3.y;
+        a2 += (u64)v0 * w0.z + (u64)v1 * w1.z + (u64)v2 * w2.z + (u64)v3 * w3.z;
+        a3 += (u64)v0 * w0.w + (u64)v1 * w1.w + (u64)v2 * w2.w + (u64)v3 * w3.w;
+        a0 = m31_red64(a0); a1 = m31_red64(a1); a2 = m31_red64(a2); a3 = m31_red64(a3);
+      }
+    }
     for (; j + 4 <= nj; j += 4) {
       const u32 v0 = __ldg(c + ((size_t)j << LB) + t), v1 = __ldg(c + ((size_t)(j + 1) << LB) + t);
       const u32 v2 = __ldg(c + ((size_t)(j + 2) << LB) + t), v3 = __ldg(c + ((size_t)(j + 3) << LB) + t);
