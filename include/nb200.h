@@ -234,6 +234,24 @@ nb200_status nb200_gen_interaction_trace(nb200_ctx*, const nb200_air*, uint32_t 
 nb200_status nb200_prove(nb200_scheme*, const nb200_air*, const uint32_t* params, size_t n_params, nb200_channel*,
                          uint8_t** proof_out, size_t* proof_len);
 
+/* ---- one PROOF over N GPUs ---------------------------------------------------------------------------------------------------
+ * Every rank calls the same sequence (the Machine::prove order, machine.rs:197-290) with its own shard; transcript, roots and proof
+ * bytes come out identical on all ranks and identical to the single-GPU proof.
+ * nb200_scheme_commit_sharded = tree_builder.extend_evals + commit for a tree whose FIRST `total_big` columns (the main component's,
+ * 2^log_size rows) are sharded: `big_shard` = this rank's nb200_shard_range of them (finalized order); `small` = the smaller batches that
+ * follow in commitment order, identical on every rank; `replicate_cols` = indices (inside the big batch) of the columns some constraint
+ * reads at a row offset (column.rs:17-19: Pc, IsPadding; the last LogUp secure column) — their LDE is kept in full on every rank;
+ * keep_eval_rows != 0 keeps this rank's trace rows of all big columns for nb200_gen_interaction_trace_sharded (trees 0 and 1).
+ * nb200_gen_interaction_trace_sharded = generate_interaction_trace of the sharded component: returns this rank's COLUMN shard of the
+ * 4 * n_logup interaction columns (input of the next nb200_scheme_commit_sharded) and the claimed sum.  Components whose columns are
+ * replicated use nb200_gen_interaction_trace.  nb200_prove then runs constraint rows, OODS, DEEP quotients and decommitment sharded,
+ * composition / FRI / PoW replicated. */
+nb200_status nb200_scheme_commit_sharded(nb200_scheme*, const nb200_cols* big_shard, size_t total_big, uint32_t log_size,
+                                         const nb200_cols* const* small, size_t n_small, const uint32_t* replicate_cols, size_t n_replicate,
+                                         int keep_eval_rows, nb200_channel*, uint8_t root[32]);
+nb200_status nb200_gen_interaction_trace_sharded(nb200_scheme*, const nb200_air*, uint32_t component, const uint32_t* params, size_t n_params,
+                                                 nb200_cols** shard_out, uint32_t claimed_sum[4]);
+
 /* ---- backend-trait level operations ---------------------------------------------------------------------
  * The per-trait surface a Rust `struct CudaBackend;` shim binds when it implements Stwo's backend traits one by one
  * instead of calling the coarse nb200_prove.  nb200_prove runs exactly this code.  A "secure column"

@@ -123,7 +123,17 @@ nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst,
 // evaluations -> coefficients + LDE (+ optionally the half-coset extension the quotient step needs) for one batch (fft_fused.cu)
 nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 log_size, u32 log_blowup);
 void fft_fused_release(nb200_ctx* ctx);
-void comm_release(nb200_ctx* ctx);   // comm.cu
+// ---- multi-GPU plumbing (comm.cu): NCCL over the ranks that prove one trace together; all no-ops / local copies without a communicator
+void comm_release(nb200_ctx* ctx);
+int comm_rank(const nb200_ctx* ctx);
+int comm_world(const nb200_ctx* ctx);
+int comm_log_world(const nb200_ctx* ctx);
+void comm_shard_range(size_t total, int world, int rank, size_t* first, size_t* count);
+nb200_status exchange_cols_to_rows(nb200_ctx* ctx, const u32* src, size_t total, size_t LEN, u32* dst_rows);
+nb200_status exchange_rows_to_cols(nb200_ctx* ctx, const u32* src_rows, size_t total, size_t LEN, u32* dst);
+nb200_status comm_all_gather_dev(nb200_ctx* ctx, const u32* mine, size_t words, u32* out);
+nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root);
+nb200_status comm_all_reduce_sum_host(nb200_ctx* ctx, u32* host, size_t words);
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
 nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32* dst, size_t n_cols, u32 log_size, int coset_order);
 // Host columns -> device evaluations -> coefficients -> LDE, in column chunks: the H2D copy of chunk k+1 (side stream)

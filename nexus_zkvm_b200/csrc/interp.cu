@@ -290,7 +290,7 @@ static nb200_status launch_interp(nb200_ctx* ctx, InterpArgs& a, u32 domain_log)
 // Evaluate the component's constraints on its evaluation domain and accumulate  sum_k coeff_k * c_k / vanishing  into acc.
 // mask_cols[m]: device pointer of mask m's column evaluated on CanonicCoset(eval_log).circle_domain().
 nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params,
-                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk, u32 rows_log, u32 dom_log) {
+                             const std::vector<qm31>& coeffs, u32* const acc[4], const JitKernel* jk, u32 rows_log, u32 dom_log, u32 row0, size_t n_rows) {
   NB_ARG(ctx, mask_cols.size() == c.masks.size() && coeffs.size() == c.n_constraints, "constraint_eval: shape");
   // rows [0, 2^rows_log) of CanonicCoset(dom_log).circle_domain() in bit-reversed order: the whole domain or its first half
   if (rows_log == 0 && dom_log == 0) rows_log = dom_log = c.eval_log();
@@ -321,6 +321,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_dinv, dinv.size() * 4));
   NB_CUDA(ctx, cudaMemcpyAsync(d_dinv, dinv.data(), dinv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   nb200_status st;
+  if (row0 != 0 || n_rows != 0) NB_ARG(ctx, jk && jk->kernel && jk->log_size == c.log_size, "constraint_eval: a row range needs the specialised kernel");
   if (jk && jk->kernel && jk->log_size == c.log_size && ((size_t)1 << rows_log) >= JIT_BLOCK) {
     // NVRTC-specialised kernel (jit.cu): same arithmetic, registers instead of the shared-memory register file
     const u32** d_cols = nullptr;
@@ -331,7 +332,7 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
     u32* d_tab = nullptr;
     NB_CUDA(ctx, dmalloc(ctx, (void**)&d_tab, tab.size() * 4 + 16));
     NB_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_tab, d_dinv, acc, rows_log, dom_log);
+    st = jit_launch_constraints(ctx, *jk, d_cols, d_params, d_tab, d_dinv, acc, rows_log, dom_log, row0, n_rows);
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, (void*)d_cols); dfree(ctx, d_tab);
   } else {
@@ -347,6 +348,8 @@ nb200_status constraint_eval(nb200_ctx* ctx, const AirComponent& c, const std::v
   dfree(ctx, d_prog); dfree(ctx, d_masks); dfree(ctx, d_coeff); dfree(ctx, d_dinv);
   return st;
 }
+
+nb200_status logup_finalize_last(nb200_ctx* ctx, u32 log_size, u32* last4, qm31* claimed);
 
 // LogupTraceGenerator: fills 4 * n_logup_cols columns (bit-reversed circle-domain order) and returns the claimed sum.
 // mask_cols[m]: device pointer of mask m's trace column on the trace domain (nullptr for masks the program never reads).
@@ -382,13 +385,31 @@ nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::ve
   } else {
     NB_TRY(launch_interp<true>(ctx, a, c.log_size));
   }
-  // finalize_last: claimed sum of the last secure column, shift by claimed/2^n, prefix sum in coset order
-  const size_t n = (size_t)1 << c.log_size;
-  u32* last = d_out + ((size_t)(4 * (ncols - 1)) << c.log_size);
+  dfree(ctx, d_prog); dfree(ctx, d_masks); dfree(ctx, d_batch);
+  return logup_finalize_last(ctx, c.log_size, d_out + ((size_t)(4 * (ncols - 1)) << c.log_size), claimed);
+}
+
+// the row kernel alone on 2^rows_log rows (a rank's slice of the trace domain): out = 4 * n_logup_cols columns of 2^rows_log rows
+nb200_status logup_rows(nb200_ctx* ctx, const AirComponent& c, const std::vector<const u32*>& mask_cols, const u32* d_params, u32* d_out, u32 rows_log, const JitKernel* jk) {
+  NB_ARG(ctx, mask_cols.size() == c.masks.size() && jk && jk->kernel && jk->log_size == c.log_size, "logup_rows: needs the specialised kernel");
+  std::vector<const u32*> ptrs(c.masks.size());
+  for (size_t m = 0; m < ptrs.size(); ++m) ptrs[m] = (c.masks[m].off == 0 && c.masks[m].tree != 2) ? mask_cols[m] : nullptr;
+  const u32** d_cols = nullptr;
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_cols, std::max<size_t>(ptrs.size(), 1) * sizeof(u32*)));
+  NB_CUDA(ctx, cudaMemcpyAsync(d_cols, ptrs.data(), ptrs.size() * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
+  nb200_status js = jit_launch_logup(ctx, *jk, d_cols, d_params, d_out, rows_log);
+  cudaStreamSynchronize(ctx->stream);
+  dfree(ctx, (void*)d_cols);
+  return js;
+}
+
+// finalize_last on the FULL last secure column (4 coordinate columns of 2^log_size rows): claimed sum, shift by claimed / 2^n, prefix sum in coset order
+nb200_status logup_finalize_last(nb200_ctx* ctx, u32 log_size, u32* last, qm31* claimed) {
+  const size_t n = (size_t)1 << log_size;
   const u32 sb = 64;
   u32* d_part = nullptr;
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_part, 4 * sb * 4));
-  sum_columns_kernel<<<dim3(sb, 4), 256, 0, ctx->stream>>>(last, c.log_size, d_part);
+  sum_columns_kernel<<<dim3(sb, 4), 256, 0, ctx->stream>>>(last, log_size, d_part);
   NB_LAUNCH_CHECK(ctx);
   std::vector<u32> part(4 * sb);
   NB_CUDA(ctx, cudaMemcpyAsync(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -401,15 +422,15 @@ nb200_status logup_generate(nb200_ctx* ctx, const AirComponent& c, const std::ve
   NB_CUDA(ctx, dmalloc(ctx, (void**)&tmp, n * 4));
   u32 thr = 256, blk = (u32)((n + thr - 1) / thr);
   for (int k = 0; k < 4; ++k) {
-    u32* col = last + ((size_t)k << c.log_size);
-    coset_gather_shift_kernel<<<blk, thr, 0, ctx->stream>>>(col, c.log_size, shift.c[k], tmp);
+    u32* col = last + ((size_t)k << log_size);
+    coset_gather_shift_kernel<<<blk, thr, 0, ctx->stream>>>(col, log_size, shift.c[k], tmp);
     NB_LAUNCH_CHECK(ctx);
     NB_TRY(inclusive_scan(ctx, tmp, n));
-    coset_scatter_kernel<<<blk, thr, 0, ctx->stream>>>(tmp, c.log_size, col);
+    coset_scatter_kernel<<<blk, thr, 0, ctx->stream>>>(tmp, log_size, col);
     NB_LAUNCH_CHECK(ctx);
   }
   cudaStreamSynchronize(ctx->stream);
-  dfree(ctx, tmp); dfree(ctx, d_part); dfree(ctx, d_prog); dfree(ctx, d_masks); dfree(ctx, d_batch);
+  dfree(ctx, tmp); dfree(ctx, d_part);
   return NB200_OK;
 }
 

@@ -241,8 +241,8 @@ std::string gen_source(const AirComponent& c) {
   // code at a time and the instruction cache serves them from one fetch.  Without the barriers the warps drift apart over the ~0.7 MB
   // program and the kernel is instruction-fetch bound (ncu: stall_no_instruction 11 per issue, icc hit rate 53 %).
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
-    << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL) {\n"
-    << "  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;\n  St s;\n"
+    << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL, u32 row0) {\n"
+    << "  const u32 row = row0 + blockIdx.x * blockDim.x + threadIdx.x;   // row0: a rank of a multi-GPU proof evaluates its slice of the domain's rows\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
   for (size_t ci = 0; ci < n_chunks; ++ci) o << "  chunk" << ci << "(s, cols, params, coeff, row, EL);\n  __syncthreads();\n";
   o << "  const u32 di = __ldg(dinv + (row >> " << DL << "));\n"
@@ -366,7 +366,7 @@ uint64_t jit_source_key(const std::string& src) {
   uint64_t h = 1469598103934665603ull;
   auto mix = [&](const char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } };
   mix(src.data(), src.size());
-  const char* tgt = "|sm_100a|nb200-jit-3";
+  const char* tgt = "|sm_100a|nb200-jit-4";
   mix(tgt, strlen(tgt));
   return h;
 }
@@ -465,6 +465,7 @@ static nb200_status jit_set_cols(nb200_ctx* ctx, const JitKernel& jk, const u32*
 }
 
 nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, u32* d_out, u32 log_size) {
+  // log_size = log2 of the rows of THIS launch (the whole trace domain, or a rank's slice of it: the kernel is row-local)
   size_t rows = (size_t)1 << log_size;
   if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
   NB_TRY(jit_set_cols(ctx, jk, d_cols));
@@ -476,13 +477,13 @@ nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* co
 }
 
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff, const u32* d_dinv, u32* const acc[4],
-                                    u32 rows_log, u32 dom_log) {
-  size_t rows = (size_t)1 << rows_log;
-  if (rows < JIT_BLOCK) return set_err(ctx, NB200_ERR_STATE, "jit: domain too small");
+                                    u32 rows_log, u32 dom_log, u32 row0, size_t n_rows) {
+  size_t rows = n_rows ? n_rows : (size_t)1 << rows_log;
+  if (rows < JIT_BLOCK || rows % JIT_BLOCK != 0) return set_err(ctx, NB200_ERR_STATE, "jit: row range too small");
   NB_TRY(jit_set_cols(ctx, jk, d_cols));
   u32 el = dom_log;
   u32* a0 = acc[0]; u32* a1 = acc[1]; u32* a2 = acc[2]; u32* a3 = acc[3];
-  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3, (void*)&el};
+  void* args[] = {(void*)&d_cols, (void*)&d_params, (void*)&d_coeff, (void*)&d_dinv, (void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3, (void*)&el, (void*)&row0};
   cudaError_t e = cudaLaunchKernel((const void*)jk.kernel, dim3((u32)(rows / jit_block())), dim3(jit_block()), args, 0, ctx->stream);
   ctx->launches += 1;
   if (e != cudaSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("jit launch: ") + cudaGetErrorString(e));

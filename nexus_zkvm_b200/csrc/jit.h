@@ -26,7 +26,7 @@ nb200_status jit_compile_logup(nb200_ctx* ctx, const AirComponent& c, JitKernel*
 nb200_status jit_launch_logup(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, u32* d_out, u32 log_size);
 std::string jit_logup_source(const AirComponent& c);
 nb200_status jit_launch_constraints(nb200_ctx* ctx, const JitKernel& jk, const u32* const* d_cols, const u32* d_params, const u32* d_coeff,
-                                    const u32* d_dinv, u32* const acc[4], u32 rows_log, u32 dom_log);
+                                    const u32* d_dinv, u32* const acc[4], u32 rows_log, u32 dom_log, u32 row0 = 0, size_t n_rows = 0);
 void jit_release(JitKernel& jk);
 void jit_coeff_table(const std::vector<qm31>& coeffs, std::vector<u32>& out);
 

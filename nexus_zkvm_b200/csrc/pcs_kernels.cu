@@ -54,9 +54,9 @@ nb200_status domain_points(nb200_ctx* ctx, u32 log_size, u32* d_x, u32* d_y) {
 // ---- DEEP quotients ----
 __global__ void __launch_bounds__(256) quotients_kernel(const QBatchDev* __restrict__ batches, u32 n_batches, const QEntryDev* __restrict__ entries,
                                                         const u32* __restrict__ dom_x, const u32* __restrict__ dom_y, u32 log_size,
-                                                        u32* __restrict__ o0, u32* __restrict__ o1, u32* __restrict__ o2, u32* __restrict__ o3) {
-  const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (1u << log_size)) return;
+                                                        u32* __restrict__ o0, u32* __restrict__ o1, u32* __restrict__ o2, u32* __restrict__ o3, u32 row0, u32 row_end) {
+  const u32 row = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= row_end) return;
   const u32 x = __ldg(dom_x + row), y = __ldg(dom_y + row);
   qm31 acc = qm31_zero();
   for (u32 b = 0; b < n_batches; ++b) {
@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(256) quotients_kernel(const QBatchDev* __restr
 // constants are fetched once for four rows.  Same arithmetic as quotients_kernel.
 __global__ void __launch_bounds__(128) quotients_kernel_x4(const QBatchDev* __restrict__ batches, u32 n_batches, const QEntryDev* __restrict__ entries,
                                                            const u32* __restrict__ dom_x, const u32* __restrict__ dom_y, u32 log_size,
-                                                           u32* __restrict__ o0, u32* __restrict__ o1, u32* __restrict__ o2, u32* __restrict__ o3) {
-  const u32 row = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  if (row >= (1u << log_size)) return;
+                                                           u32* __restrict__ o0, u32* __restrict__ o1, u32* __restrict__ o2, u32* __restrict__ o3, u32 row0, u32 row_end) {
+  const u32 row = row0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (row >= row_end) return;
   const uint4 xv = __ldg(reinterpret_cast<const uint4*>(dom_x + row)), yv = __ldg(reinterpret_cast<const uint4*>(dom_y + row));
   const u32 xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
   qm31 acc[4] = {qm31_zero(), qm31_zero(), qm31_zero(), qm31_zero()};
@@ -191,23 +191,25 @@ __global__ void __launch_bounds__(128) quotients_kernel_x4(const QBatchDev* __re
 }
 
 nb200_status quotients_launch(nb200_ctx* ctx, const QBatchDev* h_batches, size_t n_batches, const QEntryDev* h_entries, size_t n_entries,
-                              const u32* dom_x, const u32* dom_y, u32 log_size, u32* out /* 4 columns */) {
+                              const u32* dom_x, const u32* dom_y, u32 log_size, u32* out /* 4 columns */, u32 row0, size_t n_rows) {
   QBatchDev* d_b = nullptr; QEntryDev* d_e = nullptr;
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_b, n_batches * sizeof(QBatchDev)));
   NB_CUDA(ctx, dmalloc(ctx, (void**)&d_e, n_entries * sizeof(QEntryDev)));
   NB_CUDA(ctx, cudaMemcpyAsync(d_b, h_batches, n_batches * sizeof(QBatchDev), cudaMemcpyHostToDevice, ctx->stream));
   NB_CUDA(ctx, cudaMemcpyAsync(d_e, h_entries, n_entries * sizeof(QEntryDev), cudaMemcpyHostToDevice, ctx->stream));
   size_t n = (size_t)1 << log_size;
-  bool aligned = log_size >= 2 && ((((uintptr_t)out) | ((uintptr_t)dom_x) | ((uintptr_t)dom_y)) & 15u) == 0;
+  const size_t nr = n_rows ? n_rows : n;      // rows [row0, row0 + nr) of the domain (a rank's slice in a multi-GPU proof); pointers are indexed by the global row
+  const u32 row_end = (u32)(row0 + nr);
+  bool aligned = log_size >= 2 && (row0 % 4 == 0) && (nr % 4 == 0) && ((((uintptr_t)out) | ((uintptr_t)dom_x) | ((uintptr_t)dom_y)) & 15u) == 0;
   for (size_t e = 0; e < n_entries && aligned; ++e) aligned = (((uintptr_t)h_entries[e].col) & 15u) == 0;
   if (aligned) {
-    u32 thr = 128; size_t nt = n / 4;
+    u32 thr = 128; size_t nt = nr / 4;
     quotients_kernel_x4<<<(u32)((nt + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
-                                                                             out, out + n, out + 2 * n, out + 3 * n);
+                                                                             out, out + n, out + 2 * n, out + 3 * n, row0, row_end);
   } else {
     u32 thr = 256;
-    quotients_kernel<<<(u32)((n + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
-                                                                          out, out + n, out + 2 * n, out + 3 * n);
+    quotients_kernel<<<(u32)((nr + thr - 1) / thr), thr, 0, ctx->stream>>>(d_b, (u32)n_batches, d_e, dom_x, dom_y, log_size,
+                                                                          out, out + n, out + 2 * n, out + 3 * n, row0, row_end);
   }
   NB_LAUNCH_CHECK(ctx);
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -34,6 +34,19 @@ struct SchemeTree {
   nb200_tree* merkle = nullptr;
   const u32* coeff_ptr(size_t g) const { return coeffs[cols[g].batch]->col(cols[g].idx); }
   const u32* lde_ptr(size_t g) const { return ldes[cols[g].batch]->col(cols[g].idx); }
+  // ---- one proof over N GPUs (nb200_scheme_commit_sharded): the tree's FIRST `big_total` columns (2^big_log rows each: the main component's)
+  // are sharded — this rank holds the coefficients of its own column range and, for ALL of them, its slice of the LDE rows (and of the D2 rows);
+  // the smaller columns that follow are replicated in coeffs / ldes / half_ext as usual.  cols[g].batch == BIG marks a sharded column.
+  static constexpr u32 BIG = 0xffffffffu;
+  bool sharded = false;
+  size_t big_total = 0, own_first = 0, own_count = 0;
+  u32 big_log = 0;                              // polynomial log size n; LDE log m = n + blow-up; rows per rank S = 2^m / world
+  nb200_cols* big_coeffs = nullptr;             // own_count x 2^n
+  nb200_cols* big_rows = nullptr;               // big_total x S: LDE rows [rank * S, (rank + 1) * S)
+  nb200_cols* big_rows_hx = nullptr;            // big_total x S: the same rows of the half-coset extension D2 (or nullptr)
+  nb200_cols* big_eval_rows = nullptr;          // big_total x 2^n / world: trace-domain rows (kept for the interaction trace of trees 0 / 1)
+  std::map<size_t, nb200_cols*> full_lde, full_hx;   // columns read at a row offset: full LDE / D2 copies on every rank
+  std::vector<std::vector<uint8_t>> top_layers; // host copies of the Merkle layers 0..k (layer k = the world caps); `merkle` is this rank's sub-tree
 };
 
 }  // namespace nb
@@ -48,6 +61,8 @@ struct nb200_scheme {
 extern "C" nb200_status nb200_cols_alloc(nb200_ctx*, size_t, uint32_t, nb200_cols**);
 extern "C" void nb200_cols_free(nb200_ctx*, nb200_cols*);
 extern "C" void nb200_tree_free(nb200_ctx*, nb200_tree*);
+extern "C" nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t* right, const uint32_t* values, size_t n_values, uint8_t out[32]);
+namespace nb { nb200_status gather_hash(nb200_ctx* ctx, const std::vector<const uint8_t*>& addrs, uint8_t* host_out); }
 
 namespace nb {
 
@@ -60,6 +75,9 @@ struct ColsGuard {
 };
 
 static void free_tree(nb200_ctx* ctx, SchemeTree& t) {
+  for (nb200_cols* c : {t.big_coeffs, t.big_rows, t.big_rows_hx, t.big_eval_rows}) if (c) nb200_cols_free(ctx, c);
+  for (auto& kv : t.full_lde) nb200_cols_free(ctx, kv.second);
+  for (auto& kv : t.full_hx) nb200_cols_free(ctx, kv.second);
   for (auto* c : t.coeffs) nb200_cols_free(ctx, c);
   for (auto* c : t.ldes) nb200_cols_free(ctx, c);
   for (auto* c : t.half_ext) if (c) nb200_cols_free(ctx, c);
@@ -167,6 +185,211 @@ nb200_status scheme_commit_host(nb200_scheme* s, const void* const* host, const 
   trace_mark(ctx, "commit: merkle");
   if (root) memcpy(root, t.merkle->root, 32);
   s->trees.push_back(std::move(t));
+  return NB200_OK;
+}
+
+// ======================================================================================================================================
+// One PROOF over N GPUs (BASELINE configs[3]).  Every rank calls the same sequence; transcript, roots and proof bytes are
+// identical on all ranks and identical to the single-GPU proof.  Sharding: the main component's columns (the tree's first, largest batch) are
+// column-sharded for the transforms and OODS evaluation and row-sharded for hashing, constraint rows and DEEP quotients, with one NVLink
+// exchange per committed tree and evaluation set (comm.cu); the few columns read at a row offset (`Pc`, `IsPadding`, the last LogUp column) are
+// replicated; everything small (extension components, composition tree, FRI) is computed redundantly on every rank.
+// ======================================================================================================================================
+static nb200_status replicate_column(nb200_ctx* ctx, const nb200_cols* own_cols /* own_count x LEN */, size_t own_first, size_t own_count, size_t g, size_t total,
+                                     u32 log_len, nb200_cols** out) {
+  NB_TRY(nb200_cols_alloc(ctx, 1, log_len, out));
+  int owner = 0;
+  for (int r = 0; r < comm_world(ctx); ++r) { size_t f, c; comm_shard_range(total, comm_world(ctx), r, &f, &c); if (g >= f && g < f + c) owner = r; }
+  if (g >= own_first && g < own_first + own_count)
+    NB_CUDA(ctx, cudaMemcpyAsync((*out)->d, own_cols->col(g - own_first), ((size_t)4) << log_len, cudaMemcpyDeviceToDevice, ctx->stream));
+  return comm_broadcast_dev(ctx, (*out)->d, (size_t)1 << log_len, owner);
+}
+
+nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard, size_t total_big, u32 n, const nb200_cols* const* small, size_t n_small,
+                                   const u32* replicate, size_t n_replicate, int keep_eval_rows, HostChannel& ch, uint8_t root[32]) {
+  nb200_ctx* ctx = s->ctx;
+  const int world = comm_world(ctx), rank = comm_rank(ctx);
+  const u32 k = (u32)comm_log_world(ctx), bl = s->log_blowup, m = n + bl;
+  NB_ARG(ctx, m >= k + 10, "commit_sharded: the sharded columns need at least 1024 LDE rows per rank");
+  for (size_t b = 0; b < n_small; ++b) NB_ARG(ctx, small[b] && small[b]->log_size < n, "commit_sharded: replicated batches must be smaller than the sharded columns");
+  size_t first = 0, count = 0;
+  comm_shard_range(total_big, world, rank, &first, &count);
+  NB_ARG(ctx, (count == 0 && (!big_shard || big_shard->n_cols == 0)) || (big_shard && big_shard->n_cols == count && big_shard->log_size == n),
+         "commit_sharded: the column shard must be nb200_shard_range(total, world, rank) columns of 2^log_size rows");
+  const bool want_hx = (s->hint_log_expand == bl + 1);
+  NB_TRY(twiddles_prepare(ctx, want_hx ? m + 1 : m));
+  trace_mark(ctx, nullptr);
+  SchemeTree t;
+  t.sharded = true; t.big_total = total_big; t.own_first = first; t.own_count = count; t.big_log = n;
+  nb200_cols *lde_full = nullptr, *hx_full = nullptr;
+  auto fail = [&](nb200_status st) { if (lde_full) nb200_cols_free(ctx, lde_full); if (hx_full) nb200_cols_free(ctx, hx_full); free_tree(ctx, t); return st; };
+#define NB_TRYS(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail(_s); } while (0)
+  // 1. column-sharded transforms of this rank's columns
+  NB_TRYS(nb200_cols_alloc(ctx, count, n, &t.big_coeffs));
+  NB_TRYS(nb200_cols_alloc(ctx, count, m, &lde_full));
+  if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, count, m, &hx_full));
+  if (count) NB_TRYS(commit_transforms(ctx, big_shard->d, t.big_coeffs->d, lde_full->d, hx_full ? hx_full->d : nullptr, count, n, bl));
+  trace_mark(ctx, "sharded commit: ifft+lde (own columns)");
+  // 2. exchange: columns -> row slices (LDE, D2, and the trace rows the interaction trace will read)
+  NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows));
+  NB_TRYS(exchange_cols_to_rows(ctx, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d));
+  if (want_hx) {
+    NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows_hx));
+    NB_TRYS(exchange_cols_to_rows(ctx, hx_full->d, total_big, (size_t)1 << m, t.big_rows_hx->d));
+  }
+  if (keep_eval_rows) {
+    NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
+    NB_TRYS(exchange_cols_to_rows(ctx, count ? big_shard->d : nullptr, total_big, (size_t)1 << n, t.big_eval_rows->d));
+  }
+  // 3. columns that constraints read at a row offset: full copies everywhere
+  for (size_t i = 0; i < n_replicate; ++i) {
+    const size_t g = replicate[i];
+    if (g >= total_big) return fail(set_err(ctx, NB200_ERR_ARG, "commit_sharded: replicate index out of range"));
+    if (t.full_lde.count(g)) continue;
+    nb200_cols* f = nullptr;
+    NB_TRYS(replicate_column(ctx, lde_full, first, count, g, total_big, m, &f));
+    t.full_lde[g] = f;
+    if (want_hx) { nb200_cols* h = nullptr; NB_TRYS(replicate_column(ctx, hx_full, first, count, g, total_big, m, &h)); t.full_hx[g] = h; }
+  }
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  nb200_cols_free(ctx, lde_full); lde_full = nullptr;
+  if (hx_full) { nb200_cols_free(ctx, hx_full); hx_full = nullptr; }
+  trace_mark(ctx, "sharded commit: exchange");
+  // 4. the smaller batches: computed in full by every rank
+  for (size_t b = 0; b < n_small; ++b) {
+    nb200_cols *co = nullptr, *lde = nullptr, *hx = nullptr;
+    NB_TRYS(nb200_cols_alloc(ctx, small[b]->n_cols, small[b]->log_size, &co));
+    t.coeffs.push_back(co);
+    NB_TRYS(nb200_cols_alloc(ctx, small[b]->n_cols, small[b]->log_size + bl, &lde));
+    t.ldes.push_back(lde);
+    if (want_hx && lde->log_size > 8) NB_TRYS(nb200_cols_alloc(ctx, small[b]->n_cols, lde->log_size, &hx));
+    t.half_ext.push_back(hx);
+    NB_TRYS(commit_transforms(ctx, small[b]->d, co->d, lde->d, hx ? hx->d : nullptr, co->n_cols, co->log_size, bl));
+  }
+  // 5. row-sharded sub-tree, caps, top levels
+  const size_t S = (size_t)1 << (m - k);
+  std::vector<ColRef> refs;
+  t.cols.clear();
+  for (size_t g = 0; g < total_big; ++g) { refs.push_back(ColRef{t.big_rows->d + g * S, m - k}); t.cols.push_back(SchemeTree::ColLoc{SchemeTree::BIG, (u32)g, n}); }
+  struct TopCol { u32 log; std::vector<u32> vals; };
+  std::vector<TopCol> top;
+  for (size_t b = 0; b < t.ldes.size(); ++b)
+    for (size_t c2 = 0; c2 < t.ldes[b]->n_cols; ++c2) {
+      const u32 sl = t.ldes[b]->log_size;
+      t.cols.push_back(SchemeTree::ColLoc{(u32)b, (u32)c2, t.coeffs[b]->log_size});
+      if (sl >= k) refs.push_back(ColRef{t.ldes[b]->col(c2) + ((size_t)rank << (sl - k)), sl - k});
+      else {
+        TopCol tc; tc.log = sl; tc.vals.resize((size_t)1 << sl);
+        NB_CUDA(ctx, cudaMemcpyAsync(tc.vals.data(), t.ldes[b]->col(c2), tc.vals.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        top.push_back(std::move(tc));
+      }
+    }
+  NB_TRYS(merkle_commit(ctx, refs, &t.merkle));
+  NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  t.top_layers.assign(k + 1, {});
+  t.top_layers[k].resize((size_t)32 << k);
+  {
+    std::vector<u32> mine(8), all((size_t)8 * world);
+    memcpy(mine.data(), t.merkle->root, 32);
+    u32* d = nullptr;
+    NB_CUDA(ctx, dmalloc(ctx, (void**)&d, (size_t)32 * (world + 1)));
+    NB_CUDA(ctx, cudaMemcpyAsync(d, mine.data(), 32, cudaMemcpyHostToDevice, ctx->stream));
+    nb200_status st = comm_all_gather_dev(ctx, d, 8, d + 8);
+    if (st == NB200_OK && cudaMemcpyAsync(t.top_layers[k].data(), d + 8, (size_t)32 * world, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "caps d2h");
+    if (st == NB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "caps sync");
+    dfree(ctx, d);
+    if (st != NB200_OK) return fail(st);
+  }
+  for (u32 l = k; l-- > 0;) {
+    t.top_layers[l].resize((size_t)32 << l);
+    for (size_t i = 0; i < ((size_t)1 << l); ++i) {
+      std::vector<u32> vals;
+      for (auto& tc : top) if (tc.log == l) vals.push_back(tc.vals[i]);
+      NB_TRYS(nb200_hash_node(ctx->merkle_hash, &t.top_layers[l + 1][64 * i], &t.top_layers[l + 1][64 * i + 32], vals.data(), vals.size(), &t.top_layers[l][32 * i]));
+    }
+  }
+  memcpy(t.merkle->root, t.top_layers[0].data(), 32);   // from here on `merkle->root` is the root of the WHOLE tree (the sub-tree's own root is top_layers[k][rank])
+#undef NB_TRYS
+  trace_mark(ctx, "sharded commit: merkle + caps");
+  ch.mix_root(t.merkle->root);
+  if (root) memcpy(root, t.merkle->root, 32);
+  s->trees.push_back(std::move(t));
+  return NB200_OK;
+}
+
+// MerkleProver::decommit of a sharded tree: the same walk as merkle_decommit; every value / hash it names is owned by exactly one rank (a row
+// slice, a sub-tree node) or known to all (replicated columns, the top layers): owners fill their words, one all-reduce merges them.
+static nb200_status merkle_decommit_sharded(nb200_ctx* ctx, const SchemeTree& t, u32 blow, const std::vector<std::pair<u32, std::vector<u64>>>& queries,
+                                            std::vector<u32>& queried_values, std::vector<uint8_t>& hash_witness, std::vector<u32>& column_witness) {
+  const u32 k = (u32)comm_log_world(ctx);
+  const int rank = comm_rank(ctx);
+  const u32 m = t.big_log + blow;
+  const size_t S = (size_t)1 << (m - k);
+  struct CRef { const u32* d; u32 log; bool big; };   // big: d = row-slice base of this rank; else a full replicated column
+  std::vector<CRef> cols;
+  for (size_t g = 0; g < t.cols.size(); ++g) {
+    if (t.cols[g].batch == SchemeTree::BIG) cols.push_back(CRef{t.big_rows->d + (size_t)t.cols[g].idx * S, m, true});
+    else cols.push_back(CRef{t.ldes[t.cols[g].batch]->col(t.cols[g].idx), t.ldes[t.cols[g].batch]->log_size, false});
+  }
+  std::stable_sort(cols.begin(), cols.end(), [](const CRef& a, const CRef& b) { return a.log > b.log; });
+  std::vector<const u32*> val_addrs; std::vector<size_t> val_slot; std::vector<uint8_t> val_is_query;
+  std::vector<const uint8_t*> hash_addrs; std::vector<size_t> hash_slot;
+  std::vector<u32> vals; std::vector<uint8_t> hashes;
+  size_t ci = 0;
+  std::vector<u64> last_layer_queries;
+  for (int l = (int)m; l >= 0; --l) {
+    std::vector<u64> layer_total;
+    size_t firstc = ci;
+    while (ci < cols.size() && cols[ci].log == (u32)l) ++ci;
+    const std::vector<u64>* lq = nullptr;
+    for (auto& q : queries) if (q.first == (u32)l) lq = &q.second;
+    size_t pq = 0, cq = 0;
+    size_t nlq = lq ? lq->size() : 0;
+    auto want_hash = [&](u64 child) {   // node `child` of layer l + 1
+      const u32 cl = (u32)l + 1;
+      const size_t slot = hashes.size() / 32;
+      hashes.resize(hashes.size() + 32, 0);
+      if (cl <= k) { if (rank == 0) memcpy(&hashes[32 * slot], &t.top_layers[cl][32 * child], 32); }      // known to all: rank 0 contributes
+      else if ((child >> (cl - k)) == (u64)rank) { hash_addrs.push_back(t.merkle->layer[cl - k] + 32 * (child & (((u64)1 << (cl - k)) - 1))); hash_slot.push_back(slot); }
+    };
+    while (true) {
+      bool has_p = pq < last_layer_queries.size(), has_c = cq < nlq;
+      if (!has_p && !has_c) break;
+      u64 node;
+      if (has_p && has_c) node = std::min(last_layer_queries[pq] / 2, (*lq)[cq]);
+      else if (has_p) node = last_layer_queries[pq] / 2;
+      else node = (*lq)[cq];
+      if ((u32)l < m) {
+        if (pq < last_layer_queries.size() && last_layer_queries[pq] == 2 * node) ++pq; else want_hash(2 * node);
+        if (pq < last_layer_queries.size() && last_layer_queries[pq] == 2 * node + 1) ++pq; else want_hash(2 * node + 1);
+      }
+      bool queried = cq < nlq && (*lq)[cq] == node;
+      if (queried) ++cq;
+      for (size_t c = firstc; c < ci; ++c) {
+        const size_t slot = vals.size();
+        vals.push_back(0u); val_is_query.push_back(queried ? 1 : 0);
+        if (cols[c].big) { if ((node >> (m - k)) == (u64)rank) { val_addrs.push_back(cols[c].d + (node & (S - 1))); val_slot.push_back(slot); } }
+        else if (rank == 0) { val_addrs.push_back(cols[c].d + node); val_slot.push_back(slot); }
+      }
+      layer_total.push_back(node);
+    }
+    last_layer_queries.swap(layer_total);
+  }
+  std::vector<u32> got(val_addrs.size());
+  NB_TRY(gather_u32(ctx, val_addrs, got.data()));
+  for (size_t i = 0; i < got.size(); ++i) vals[val_slot[i]] = got[i];
+  std::vector<uint8_t> goth(hash_addrs.size() * 32);
+  NB_TRY(gather_hash(ctx, hash_addrs, goth.data()));
+  for (size_t i = 0; i < hash_addrs.size(); ++i) memcpy(&hashes[32 * hash_slot[i]], &goth[32 * i], 32);
+  // merge: exactly one rank filled each word
+  std::vector<u32> buf(vals.size() + hashes.size() / 4);
+  memcpy(buf.data(), vals.data(), vals.size() * 4);
+  if (!hashes.empty()) memcpy(buf.data() + vals.size(), hashes.data(), hashes.size());
+  NB_TRY(comm_all_reduce_sum_host(ctx, buf.data(), buf.size()));
+  queried_values.clear(); column_witness.clear();
+  for (size_t i = 0; i < vals.size(); ++i) (val_is_query[i] ? queried_values : column_witness).push_back(buf[i]);
+  hash_witness.resize(hashes.size());
+  if (!hashes.empty()) memcpy(hash_witness.data(), buf.data() + vals.size(), hashes.size());
   return NB200_OK;
 }
 
@@ -362,6 +585,49 @@ nb200_status component_quotients(nb200_scheme* s, nb200_air* air_h, size_t comp_
   return st;
 }
 
+static bool component_is_sharded(const nb200_scheme* s, const AirComponent& c) {
+  for (const AirMask& mk : c.masks)
+    if (mk.tree < s->trees.size() && s->trees[mk.tree].sharded && mk.col < s->trees[mk.tree].cols.size() && s->trees[mk.tree].cols[mk.col].batch == SchemeTree::BIG) return true;
+  return false;
+}
+
+// evaluate_constraint_quotients_on_domain of the sharded (main) component: this rank evaluates ITS rows of D1 (from the LDE row slices) and of D2
+// (from the D2 row slices) — masks at a row offset read the replicated full columns — and the accumulator columns are all-gathered in place.
+static nb200_status component_quotients_sharded(nb200_scheme* s, nb200_air* air_h, size_t comp_idx, const u32* d_params, const std::vector<qm31>& coeff,
+                                                nb200_cols* accum, nb200_cols* accum_hi) {
+  nb200_ctx* ctx = s->ctx;
+  const AirComponent& c = air_h->prog.comps[comp_idx];
+  const u32 elog = c.eval_log(), lde_log = c.log_size + s->log_blowup, k = (u32)comm_log_world(ctx);
+  NB_ARG(ctx, elog == lde_log + 1 && accum && accum_hi && accum->log_size == lde_log && accum_hi->log_size == lde_log, "sharded constraint quotients: the component must use the half-domain route");
+  NB_ARG(ctx, coeff.size() == c.n_constraints, "constraint quotients: one coefficient per constraint");
+  const size_t S = (size_t)1 << (lde_log - k);
+  const u32 row0 = (u32)(comm_rank(ctx) * S);
+  std::vector<const u32*> m_lde(c.masks.size()), m_hx(c.masks.size());
+  for (size_t m = 0; m < c.masks.size(); ++m) {
+    const AirMask& mk = c.masks[m];
+    NB_ARG(ctx, mk.tree < s->trees.size() && mk.col < s->trees[mk.tree].cols.size(), "prove: AIR references a column that was not committed");
+    const SchemeTree& tr = s->trees[mk.tree];
+    const SchemeTree::ColLoc& loc = tr.cols[mk.col];
+    NB_ARG(ctx, tr.sharded && loc.batch == SchemeTree::BIG && loc.log == c.log_size && tr.big_rows_hx, "sharded constraint quotients: the component may only read sharded columns of its own size");
+    if (mk.off == 0) { m_lde[m] = tr.big_rows->d + (size_t)loc.idx * S - row0; m_hx[m] = tr.big_rows_hx->d + (size_t)loc.idx * S - row0; }   // indexed by the GLOBAL row
+    else {
+      auto f = tr.full_lde.find(loc.idx); auto h = tr.full_hx.find(loc.idx);
+      NB_ARG(ctx, f != tr.full_lde.end() && h != tr.full_hx.end(), "sharded constraint quotients: a column read at a row offset was not listed for replication at commit time");
+      m_lde[m] = f->second->d; m_hx[m] = h->second->d;
+    }
+  }
+  JitKernel& jk = air_h->jit[comp_idx];
+  if (!jk.tried) { jk.tried = true; if (jit_enabled()) jit_compile_constraints(ctx, c, &jk); }
+  NB_ARG(ctx, jk.kernel != nullptr, "sharded constraint quotients need the specialised kernel");
+  u32* lo[4] = {accum->col(0), accum->col(1), accum->col(2), accum->col(3)};
+  u32* hi[4] = {accum_hi->col(0), accum_hi->col(1), accum_hi->col(2), accum_hi->col(3)};
+  NB_TRY(constraint_eval(ctx, c, m_lde, d_params, coeff, lo, &jk, lde_log, lde_log, row0, S));
+  NB_TRY(constraint_eval(ctx, c, m_hx, d_params, coeff, hi, &jk, lde_log, elog, row0, S));
+  for (int q = 0; q < 4; ++q) { NB_TRY(comm_all_gather_dev(ctx, lo[q] + row0, S, lo[q])); NB_TRY(comm_all_gather_dev(ctx, hi[q] + row0, S, hi[q])); }
+  trace_mark(ctx, "constraints: row kernel (sharded) + all-gather");
+  return NB200_OK;
+}
+
 // coefficients (4 columns of 2^elog, circle-FFT basis) of the quotient polynomial held by a Q_HALF accumulator pair; lo/hi are consumed
 static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* hi, u32 elog, u32* out /* 4 columns */, size_t out_stride /* >= 2^elog */) {
   const u32 h = elog - 1;
@@ -381,7 +647,7 @@ static nb200_status half_to_coeffs(nb200_ctx* ctx, nb200_cols* lo, nb200_cols* h
 
 // QuotientOps::accumulate_quotients on CanonicCoset(log_size).circle_domain(): out (4 columns) = sum over the sample batches
 struct SampleBatch { qpoint p; std::vector<std::pair<const u32*, qm31>> cols; };
-nb200_status accumulate_quotients(nb200_ctx* ctx, u32 lg, const std::vector<SampleBatch>& hb, qm31 q_coeff, u32* out) {
+nb200_status accumulate_quotients(nb200_ctx* ctx, u32 lg, const std::vector<SampleBatch>& hb, qm31 q_coeff, u32* out, u32 row0 = 0, size_t n_rows = 0) {
   std::vector<QBatchDev> qb(hb.size()); std::vector<QEntryDev> qe;
   for (size_t b = 0; b < hb.size(); ++b) {
     QBatchDev& B = qb[b];
@@ -408,7 +674,7 @@ nb200_status accumulate_quotients(nb200_ctx* ctx, u32 lg, const std::vector<Samp
   ColsGuard dom(ctx);
   NB_TRY(nb200_cols_alloc(ctx, 2, lg, &dom.c));
   NB_TRY(domain_points(ctx, lg, dom.c->col(0), dom.c->col(1)));
-  return quotients_launch(ctx, qb.data(), qb.size(), qe.data(), qe.size(), dom.c->col(0), dom.c->col(1), lg, out);
+  return quotients_launch(ctx, qb.data(), qb.size(), qe.data(), qe.size(), dom.c->col(0), dom.c->col(1), lg, out, row0, n_rows);
 }
 
 // stwo::prover::prove
@@ -456,7 +722,8 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     if (st == NB200_OK) {
       std::vector<qm31> coeff(c.n_constraints);
       for (u32 k = 0; k < c.n_constraints; ++k) coeff[k] = powers[n_total - 1 - (g0 + k)];
-      st = component_quotients(s, air_h, &c - &air.comps[0], d_params, coeff, mode, acc[key].a, acc[key].b);
+      if (component_is_sharded(s, c)) st = component_quotients_sharded(s, air_h, &c - &air.comps[0], d_params, coeff, acc[key].a, acc[key].b);
+      else st = component_quotients(s, air_h, &c - &air.comps[0], d_params, coeff, mode, acc[key].a, acc[key].b);
     }
     g0 += c.n_constraints;
     if (st != NB200_OK) { free_acc(); dfree(ctx, d_params); return st; }
@@ -519,6 +786,7 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
   };
   std::vector<std::vector<std::vector<qpoint>>> points(4);
   std::vector<std::vector<std::vector<qm31>>> sampled(4);
+  std::vector<std::vector<qm31>*> sharded_samples;   // (multi-GPU) sampled-value lists of column-sharded columns, one entry per pushed value
   for (int t = 0; t < 4; ++t) {
     const SchemeTree& tr = s->trees[t];
     points[t].resize(tr.cols.size()); sampled[t].resize(tr.cols.size());
@@ -533,12 +801,30 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
       if (np > 0) {
         std::vector<u32> pts(np * 8);
         for (size_t k = 0; k < np; ++k) { memcpy(&pts[8 * k], points[t][g][k].x.c, 16); memcpy(&pts[8 * k + 4], points[t][g][k].y.c, 16); }
-        std::vector<u32> out((h - g) * np * 4);
-        NB_TRY(eval_at_points(ctx, tr.coeff_ptr(g), h - g, tr.cols[g].log, pts.data(), np, out.data()));
-        for (size_t c = g; c < h; ++c) for (size_t k = 0; k < np; ++k) sampled[t][c].push_back(load_param(&out[((c - g) * np + k) * 4]));
+        std::vector<u32> out((h - g) * np * 4, 0u);
+        if (tr.sharded && tr.cols[g].batch == SchemeTree::BIG) {
+          // column-sharded: this rank evaluates the columns whose coefficients it holds; the others stay zero until the all-reduce below
+          const size_t a = std::max<size_t>(g, tr.own_first), b2 = std::min<size_t>(h, tr.own_first + tr.own_count);
+          if (a < b2) NB_TRY(eval_at_points(ctx, tr.big_coeffs->col(a - tr.own_first), b2 - a, tr.cols[g].log, pts.data(), np, out.data() + (a - g) * np * 4));
+          for (size_t c = g; c < h; ++c) for (size_t k = 0; k < np; ++k) { sampled[t][c].push_back(load_param(&out[((c - g) * np + k) * 4])); sharded_samples.push_back(&sampled[t][c]); }
+        } else {
+          NB_TRY(eval_at_points(ctx, tr.coeff_ptr(g), h - g, tr.cols[g].log, pts.data(), np, out.data()));
+          for (size_t c = g; c < h; ++c) for (size_t k = 0; k < np; ++k) sampled[t][c].push_back(load_param(&out[((c - g) * np + k) * 4]));
+        }
       }
       g = h;
     }
+  }
+  if (!sharded_samples.empty()) {
+    // every sampled value of a sharded column was computed by exactly one rank (zero elsewhere): one all-reduce completes them.  The list holds one
+    // pointer per pushed value, in push order, so the k-th occurrence of a list is its k-th value.
+    std::map<std::vector<qm31>*, size_t> seen;
+    std::vector<u32> buf;
+    for (auto* v : sharded_samples) { const qm31& q = (*v)[seen[v]++]; buf.insert(buf.end(), q.c, q.c + 4); }
+    NB_TRY(comm_all_reduce_sum_host(ctx, buf.data(), buf.size()));
+    seen.clear();
+    size_t o = 0;
+    for (auto* v : sharded_samples) { (*v)[seen[v]++] = load_param(&buf[o]); o += 4; }
   }
   {
     std::vector<qm31> flat;
@@ -560,6 +846,7 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
     const u32 lg = all[i].log;
     // ColumnSampleBatch::new_vec: group samples by point, first-seen order                   [risk: IndexMap vs BTreeMap]
     std::vector<SampleBatch> hb;
+    bool grp_sharded = false;
     for (size_t k = i; k < j; ++k) {
       const CRef& r = all[k];
       for (size_t pi = 0; pi < points[r.t][r.g].size(); ++pi) {
@@ -567,12 +854,25 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
         size_t b = 0;
         for (; b < hb.size(); ++b) if (qm31_eq(hb[b].p.x, p.x) && qm31_eq(hb[b].p.y, p.y)) break;
         if (b == hb.size()) hb.push_back(SampleBatch{p, {}});
-        hb[b].cols.push_back({s->trees[r.t].lde_ptr(r.g), sampled[r.t][r.g][pi]});
+        const SchemeTree& trr = s->trees[r.t];
+        if (trr.sharded && trr.cols[r.g].batch == SchemeTree::BIG) {   // row slice, addressed by the global row
+          grp_sharded = true;
+          hb[b].cols.push_back({trr.big_rows->d + (size_t)trr.cols[r.g].idx * ((size_t)1 << (lg - (u32)comm_log_world(ctx))) - (size_t)comm_rank(ctx) * ((size_t)1 << (lg - (u32)comm_log_world(ctx))),
+                                sampled[r.t][r.g][pi]});
+        } else hb[b].cols.push_back({trr.lde_ptr(r.g), sampled[r.t][r.g][pi]});
       }
     }
     nb200_cols* q = nullptr;
     nb200_status st = nb200_cols_alloc(ctx, 4, lg, &q);
-    if (st == NB200_OK) { quotients.push_back(q); qlogs.push_back(lg); st = accumulate_quotients(ctx, lg, hb, q_coeff, q->d); }
+    if (st == NB200_OK) {
+      quotients.push_back(q); qlogs.push_back(lg);
+      if (grp_sharded) {   // this rank's rows of the quotient column, then an all-gather: FRI runs replicated on the whole column
+        const size_t Sg = (size_t)1 << (lg - (u32)comm_log_world(ctx));
+        const u32 r0 = (u32)(comm_rank(ctx) * Sg);
+        st = accumulate_quotients(ctx, lg, hb, q_coeff, q->d, r0, Sg);
+        for (int qq = 0; qq < 4 && st == NB200_OK; ++qq) st = comm_all_gather_dev(ctx, q->col(qq) + r0, Sg, q->col(qq));
+      } else st = accumulate_quotients(ctx, lg, hb, q_coeff, q->d);
+    }
     if (st != NB200_OK) { free_q(); dfree(ctx, d_params); return st; }
     i = j;
   }
@@ -694,8 +994,9 @@ nb200_status prove_impl(nb200_scheme* s, nb200_air* air_h, const std::vector<qm3
   std::vector<std::vector<u32>> queried_values(4); std::vector<Decommitment> decommitments(4);
   for (int t = 0; t < 4; ++t) {
     std::vector<ColRef> refs;
-    for (size_t g = 0; g < s->trees[t].cols.size(); ++g) refs.push_back(ColRef{s->trees[t].lde_ptr(g), s->trees[t].cols[g].log + blow});
-    NB_TRYF(merkle_decommit(ctx, s->trees[t].merkle, refs, by_log, queried_values[t], decommitments[t].hash_witness, decommitments[t].column_witness));
+    if (!s->trees[t].sharded) for (size_t g = 0; g < s->trees[t].cols.size(); ++g) refs.push_back(ColRef{s->trees[t].lde_ptr(g), s->trees[t].cols[g].log + blow});
+    if (s->trees[t].sharded) NB_TRYF(merkle_decommit_sharded(ctx, s->trees[t], blow, by_log, queried_values[t], decommitments[t].hash_witness, decommitments[t].column_witness));
+    else NB_TRYF(merkle_decommit(ctx, s->trees[t].merkle, refs, by_log, queried_values[t], decommitments[t].hash_witness, decommitments[t].column_witness));
   }
   cleanup_fri();
 #undef NB_TRYF
@@ -781,11 +1082,80 @@ nb200_status gen_interaction(nb200_ctx* ctx, nb200_air* air_h, u32 comp_idx, con
   return NB200_OK;
 }
 
+// LogupTraceGenerator of the sharded (main) component: this rank runs the row kernel on ITS trace rows (all columns: the row slices kept by
+// nb200_scheme_commit_sharded), the last secure column is all-gathered for the global claimed sum / coset-order prefix sum (finalize_last),
+// and one rows -> columns exchange hands every rank its COLUMN shard of the 4 * n_logup interaction columns, ready for the next sharded commit.
+nb200_status gen_interaction_sharded(nb200_scheme* s, nb200_air* air_h, u32 comp_idx, const std::vector<qm31>& params, nb200_cols** shard_out, qm31* claimed) {
+  nb200_ctx* ctx = s->ctx;
+  const AirProgram& air = air_h->prog;
+  NB_ARG(ctx, comp_idx < air.comps.size() && s->trees.size() >= 2, "gen_interaction_sharded: commit trees 0 and 1 first");
+  if (air_h->jit_logup.size() != air.comps.size()) air_h->jit_logup.resize(air.comps.size());
+  const AirComponent& c = air.comps[comp_idx];
+  const u32 n = c.log_size, k = (u32)comm_log_world(ctx);
+  const int world = comm_world(ctx), rank = comm_rank(ctx);
+  NB_ARG(ctx, n >= k + 10, "gen_interaction_sharded: at least 1024 trace rows per rank");
+  const size_t Sn = (size_t)1 << (n - k), N = (size_t)1 << n;
+  const size_t ncols = c.n_logup_cols(), total = 4 * ncols;
+  std::vector<const u32*> mask_cols(c.masks.size(), nullptr);
+  for (size_t m = 0; m < c.masks.size(); ++m) {
+    const AirMask& mk = c.masks[m];
+    if (mk.tree == 2 || mk.off != 0) continue;
+    const SchemeTree& tr = s->trees[mk.tree];
+    NB_ARG(ctx, tr.sharded && mk.col < tr.cols.size() && tr.cols[mk.col].batch == SchemeTree::BIG && tr.big_eval_rows, "gen_interaction_sharded: the component may only read sharded trace columns (commit with keep_eval_rows)");
+    mask_cols[m] = tr.big_eval_rows->d + (size_t)tr.cols[mk.col].idx * Sn;
+  }
+  JitKernel& jk = air_h->jit_logup[comp_idx];
+  if (!jk.tried) { jk.tried = true; if (jit_enabled()) jit_compile_logup(ctx, c, &jk); }
+  NB_ARG(ctx, jk.kernel != nullptr, "gen_interaction_sharded needs the specialised logup kernel");
+  u32* d_params = nullptr;
+  NB_CUDA(ctx, dmalloc(ctx, (void**)&d_params, std::max<size_t>(params.size(), 1) * 16));
+  if (!params.empty()) NB_CUDA(ctx, cudaMemcpyAsync(d_params, params.data(), params.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ColsGuard rows(ctx), last(ctx), shard(ctx);
+  nb200_status st = nb200_cols_alloc(ctx, total, n - k, &rows.c);
+  trace_mark(ctx, nullptr);
+  if (st == NB200_OK) st = logup_rows(ctx, c, mask_cols, d_params, rows.c->d, n - k, &jk);
+  // finalize_last on the whole last secure column (every rank, redundantly), then this rank's rows go back into the row batch
+  if (st == NB200_OK) st = nb200_cols_alloc(ctx, 4, n, &last.c);
+  for (int q = 0; q < 4 && st == NB200_OK; ++q) st = comm_all_gather_dev(ctx, rows.c->col(total - 4 + q), Sn, last.c->col(q));
+  if (st == NB200_OK) st = logup_finalize_last(ctx, n, last.c->d, claimed);
+  for (int q = 0; q < 4 && st == NB200_OK; ++q)
+    if (cudaMemcpyAsync(rows.c->col(total - 4 + q), last.c->col(q) + (size_t)rank * Sn, Sn * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) st = set_err(ctx, NB200_ERR_CUDA, "gen_interaction_sharded: copy");
+  trace_mark(ctx, "logup interaction trace (sharded rows)");
+  // rows -> this rank's column shard
+  size_t first = 0, count = 0;
+  comm_shard_range(total, world, rank, &first, &count);
+  if (st == NB200_OK) st = nb200_cols_alloc(ctx, count, n, &shard.c);
+  if (st == NB200_OK) st = exchange_rows_to_cols(ctx, rows.c->d, total, N, shard.c->d);
+  cudaStreamSynchronize(ctx->stream);
+  trace_mark(ctx, "logup: rows -> columns exchange");
+  dfree(ctx, d_params);
+  if (st != NB200_OK) return st;
+  *shard_out = shard.release();
+  return NB200_OK;
+}
+
 }  // namespace nb
 
 using namespace nb;
 
 extern "C" {
+
+// ---- one proof over N GPUs: commit / interaction trace (nb200_prove itself needs no sharded twin: it follows the trees it finds) ----
+nb200_status nb200_scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard, size_t total_big, uint32_t log_size, const nb200_cols* const* small, size_t n_small,
+                                         const uint32_t* replicate_cols, size_t n_replicate, int keep_eval_rows, nb200_channel* channel, uint8_t root[32]) {
+  if (!s || !channel || (n_small && !small) || (n_replicate && !replicate_cols)) return NB200_ERR_ARG;
+  return scheme_commit_sharded(s, big_shard, total_big, log_size, small, n_small, replicate_cols, n_replicate, keep_eval_rows, channel->ch, root);
+}
+nb200_status nb200_gen_interaction_trace_sharded(nb200_scheme* s, const nb200_air* air, uint32_t component, const uint32_t* params, size_t n_params,
+                                                 nb200_cols** shard_out, uint32_t claimed_sum[4]) {
+  if (!s || !air || !shard_out || !claimed_sum) return NB200_ERR_ARG;
+  std::vector<qm31> p(n_params);
+  if (n_params) memcpy(p.data(), params, n_params * 16);
+  qm31 cs;
+  NB_TRY(gen_interaction_sharded(s, const_cast<nb200_air*>(air), component, p, shard_out, &cs));
+  memcpy(claimed_sum, cs.c, 16);
+  return NB200_OK;
+}
 
 // ---- Blake2sChannel (stwo core/channel/blake2s.rs) — machine.rs:197-206,240,262 ----
 nb200_status nb200_channel_new(nb200_ctx* ctx, nb200_channel** out) {

@@ -183,6 +183,73 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", r
     return proof, claimed, aux
 
 
+def prove_sharded(machine, backend, main_cols, mult, rank, world, config=None, associated_data=b""):
+    """ONE proof by `world` GPUs (one process per GPU; `backend.ctx` holds an initialised communicator: Context.comm_init*).  Every rank calls this
+    with the same arguments and gets the same proof bytes — the bytes `prove` returns on one GPU.  The Machine::prove order (machine.rs:197-290):
+    the main component's columns (the first, largest batch of every tree) are column-sharded over the ranks for the transforms and row-sharded for
+    hashing, constraint rows and DEEP quotients; the other components' small columns are replicated.  For the harness every rank is handed the full host
+    trace and uploads only its nb200_shard_range of it (a real host would fill only that range)."""
+    from . import Context
+    config = config or dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)
+    air, ctx = machine.air, backend.ctx
+    ch = backend.channel()
+    for byte in associated_data:
+        ch.mix_u64(int(byte))
+    log_sizes = list(getattr(machine, "log_sizes", None) or [machine.log_size, 8])
+    for ls in log_sizes:
+        ch.mix_u64(ls)
+    prover = backend.prover(machine.words, config)
+    n = machine.log_size
+    main = air.components[0]
+
+    def flat(cols):
+        out = []
+        for c_ in cols:
+            a_ = np.asarray(c_)
+            out += list(a_) if a_.ndim == 2 else [a_]
+        return [np.ascontiguousarray(x, dtype=np.uint32) for x in out]
+
+    def commit_tree(t, host_cols, keep):
+        cols = flat(host_cols)
+        total_big = 0
+        while total_big < len(cols) and len(cols[total_big]) == 1 << n:
+            total_big += 1
+        assert all(len(c_) < 1 << n for c_ in cols[total_big:]), "the sharded columns must be the leading, largest batch of the tree"
+        first, count = Context.shard_range(total_big, world, rank)
+        shard = ctx.upload(np.stack(cols[first:first + count]), coset_order=True) if count else None
+        small = prover._batches_from_host(cols[total_big:], True) if len(cols) > total_big else []
+        replicate = sorted({c for (tt, c, off) in main.masks if tt == t and off != 0 and c < total_big})
+        root = prover.commit_sharded(shard, total_big, n, small, replicate, keep, ch)
+        return root, total_big, shard, small
+
+    root0, big0, shard0, small0 = commit_tree(0, machine.preprocessed_columns(), True)
+    main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)
+    root1, big1, shard1, small1 = commit_tree(1, main_part + ([mult] if mult is not None else []), True)
+    params = [(0, 0, 0, 0)] * air.n_params
+    for rel in (getattr(machine, "relations", None) or [machine.range256]):
+        rel.draw(ch, params)
+    # interaction traces: the main component sharded, the others replicated (a placeholder batch stands for the sharded columns they never read)
+    ph = [b for b in (shard0, shard1) if b is not None][0]
+    place = lambda total: ctx.wrap_device(ph.device_ptr, total, 0)
+    t0_list, t1_list = [place(big0)] + small0, [place(big1)] + small1
+    inter_small, claimed = [], []
+    shard2, cs = prover.gen_interaction_sharded(0, params)
+    claimed.append(cs)
+    params[main.cumsum_shift_param] = F.qm31_mul_m31(cs, F.m31_inv((1 << n) % P))
+    for k_, comp in enumerate(air.components[1:], start=1):
+        cols_k, cs = prover.gen_interaction_replicated(k_, comp.log_size, max(comp.batching) + 1, params, t0_list, t1_list)
+        inter_small.append(cols_k)
+        claimed.append(cs)
+        params[comp.cumsum_shift_param] = F.qm31_mul_m31(cs, F.m31_inv((1 << comp.log_size) % P))
+    ch.mix_felts(claimed)
+    big2 = 4 * (max(main.batching) + 1)
+    replicate2 = sorted({c for (tt, c, off) in main.masks if tt == 2 and off != 0})
+    root2 = prover.commit_sharded(shard2 if shard2.n_cols else None, big2, n, inter_small, replicate2, False, ch)
+    aux = {"params": params, "roots": [root0, root1, root2], "log_sizes": log_sizes, "associated_data": bytes(associated_data)}
+    proof = prover.prove(ch, params)
+    return proof, claimed, aux
+
+
 class MultiMachine:
     """A prover2-shaped machine: MANY components of DISTINCT log sizes instead of one wide component — the
     reference's prover2 builds one component per opcode family, each with its own log size (/root/reference

@@ -155,6 +155,40 @@ class CommitmentSchemeProver:
         self.tree_evals.append([Columns(self.ctx, C.c_void_p(evals[i])) for i in range(n)])
         return bytes(root)
 
+    # ---- one proof over N GPUs (ctx.comm_init first): include/nb200.h "one PROOF over N GPUs"
+    def commit_sharded(self, big_shard, total_big, log_size, small, replicate, keep_eval_rows, ch):
+        """nb200_scheme_commit_sharded.  big_shard: this rank's column range (device batch, finalized order) or None when the range is empty;
+        small: replicated device batches; replicate: indices of big columns read at a row offset."""
+        sm = (C.c_void_p * max(len(small), 1))(*[b._h for b in small])
+        rep = (C.c_uint32 * max(len(replicate), 1))(*[int(x) for x in replicate])
+        root = (C.c_uint8 * 32)()
+        self.ctx._chk(lib().nb200_scheme_commit_sharded(self._h, big_shard._h if big_shard is not None else None, C.c_size_t(total_big), C.c_uint32(log_size),
+                                                        sm, C.c_size_t(len(small)), rep, C.c_size_t(len(replicate)), C.c_int(1 if keep_eval_rows else 0), ch._h, root))
+        self.tree_evals.append(([big_shard] if big_shard is not None else []) + list(small))   # kept alive
+        return bytes(root)
+
+    def gen_interaction_sharded(self, comp, params):
+        p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
+        out = C.c_void_p()
+        claimed = np.zeros(4, np.uint32)
+        self.ctx._chk(lib().nb200_gen_interaction_trace_sharded(self._h, self.air._h, C.c_uint32(comp), p.ctypes.data_as(u32p), C.c_size_t(p.shape[0]),
+                                                                C.byref(out), claimed.ctypes.data_as(u32p)))
+        return Columns(self.ctx, out), tuple(int(x) for x in claimed)
+
+    def gen_interaction_replicated(self, comp, log_size, n_logup_cols, params, tree0, tree1):
+        """nb200_gen_interaction_trace for a component whose columns are replicated: tree0 / tree1 are batch lists that cover ALL columns of the trees
+        in commitment order (a placeholder batch stands for the sharded columns, which such a component never reads)."""
+        p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
+        a0 = (C.c_void_p * len(tree0))(*[b._h for b in tree0])
+        a1 = (C.c_void_p * len(tree1))(*[b._h for b in tree1])
+        out = C.c_void_p()
+        claimed = np.zeros(4, np.uint32)
+        self.ctx._chk(lib().nb200_gen_interaction_trace(self.ctx._h, self.air._h, C.c_uint32(comp), a0, C.c_size_t(len(tree0)), a1, C.c_size_t(len(tree1)),
+                                                        p.ctypes.data_as(u32p), C.c_size_t(p.shape[0]), C.byref(out), claimed.ctypes.data_as(u32p)))
+        cols = Columns(self.ctx, out)
+        assert cols.n_cols == 4 * n_logup_cols and cols.log_size == log_size
+        return cols, tuple(int(x) for x in claimed)
+
     def gen_interaction(self, comp, log_size, n_logup_cols, params):
         p = np.ascontiguousarray(np.array(params, dtype=np.uint32).reshape(-1, 4))
         t0, t1 = self.tree_evals[0], self.tree_evals[1]

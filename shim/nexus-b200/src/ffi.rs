@@ -81,6 +81,10 @@ extern "C" {
     pub fn nb200_commit_sharded(ctx: *mut nb200_ctx, shard_evals: *const nb200_cols, total_cols: usize, log_size: u32, log_blowup: u32,
                                 replicated: *const *const nb200_cols, n_replicated: usize, coeffs_out: *mut *mut nb200_cols, rows_out: *mut *mut nb200_cols,
                                 subtree_out: *mut *mut nb200_tree, caps_out: *mut u8, root: *mut u8) -> c_int;
+    pub fn nb200_scheme_commit_sharded(s: *mut nb200_scheme, big_shard: *const nb200_cols, total_big: usize, log_size: u32, small: *const *const nb200_cols, n_small: usize,
+                                       replicate_cols: *const u32, n_replicate: usize, keep_eval_rows: c_int, ch: *mut nb200_channel, root: *mut u8) -> c_int;
+    pub fn nb200_gen_interaction_trace_sharded(s: *mut nb200_scheme, air: *const nb200_air, component: u32, params: *const u32, n_params: usize,
+                                               shard_out: *mut *mut nb200_cols, claimed_sum: *mut u32) -> c_int;
     // ---- Blake2sChannel
     pub fn nb200_channel_new(ctx: *mut nb200_ctx, out: *mut *mut nb200_channel) -> c_int;
     pub fn nb200_channel_clone(ch: *const nb200_channel, out: *mut *mut nb200_channel) -> c_int;

@@ -41,7 +41,7 @@ extern "C" void run_rows(const unsigned* const* cols, const unsigned* params, co
                          unsigned* a0, unsigned* a1, unsigned* a2, unsigned* a3, unsigned EL, unsigned rows) {
   blockDim.x = 1; threadIdx.x = 0;
   for (unsigned i = 0; i < NB_NMASKS; ++i) ccols[i] = cols[i];   // the library fills the __constant__ table before each launch
-  for (unsigned r = 0; r < rows; ++r) { blockIdx.x = r; nbjit(cols, params, coeff, dinv, a0, a1, a2, a3, EL); }
+  for (unsigned r = 0; r < rows; ++r) { blockIdx.x = r; nbjit(cols, params, coeff, dinv, a0, a1, a2, a3, EL, 0u); }
 }
 '''
 
