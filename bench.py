@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-strong-proof", action="store_true", help="N > 1: skip the one-proof-over-all-ranks measurement")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--fft-sweep", action="store_true")
     ap.add_argument("--sweep-logs", default="16,18,20,22,24,26")
@@ -367,9 +368,11 @@ def main():
             stages, roofline = commit_breakdown(args, ctx, torch, dev, stream, m)
 
         # ---- N > 1: ONE commitment over all ranks through the library's NCCL path (strong scaling of the commit stage; not replicas)
-        strong = None
+        strong, strong_pf = None, None
         if world > 1:
             strong = strong_commit(args, ctx, torch, dist, dev, stream, rank, world, m)
+            if not args.no_strong_proof:
+                strong_pf = strong_proof(args, ctx, be, torch, dist, dev, stream, rank, world, m)
 
     verified = None
     if rank == 0 and not args.no_verify:
@@ -409,11 +412,50 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 (M31)", "data": "synthetic", "config": workload_config(args, m, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "stages": stages, "strong_commit": strong if world > 1 else None, "proof_bytes": len(last["proof"]), "verified_by_oracle_verifier": verified,
+                "stages": stages, "strong_commit": strong if world > 1 else None, "strong_proof": strong_pf if world > 1 else None, "proof_bytes": len(last["proof"]), "verified_by_oracle_verifier": verified,
                 "claimed_sums_cancel": M.verify_claimed_sums(last["claimed"]), "roots": [r.hex()[:16] for r in last["aux"]["roots"]]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_proof(args, ctx, be, torch, dist, dev, stream, rank, world, m, reps=3):
+    """ONE proof of the 2^log_rows-row machine by ALL ranks together (machine.prove_sharded: BASELINE configs[3]) — the same trace on
+    every rank (rank 0's), trees 0/1 resident as column shards, every collective inside the library.  The proof bytes are compared with the
+    single-GPU proof of the same trace computed on rank 0."""
+    from nexus_zkvm_b200 import machine as M
+    from nexus_zkvm_b200.prover import CudaBackend
+    cols, mult = fill_trace(m, 0)
+    pr = be.prover(m.words, CONFIG)
+    res = [M.shard_host_tree(m, pr, m.preprocessed_columns(), rank, world),
+           M.shard_host_tree(m, pr, list(cols) + ([mult] if mult is not None else []), rank, world)]
+    del pr
+    ts, proof = [], None
+    for rep in range(reps + 1):
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        proof, claimed, aux = M.prove_sharded(m, be, None, None, rank, world, config=CONFIG, resident=res)
+        b.record(stream)
+        torch.cuda.synchronize()
+        if rep:
+            ts.append(a.elapsed_time(b))
+    t = torch.tensor([min(ts)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    same_single = None
+    if rank == 0:
+        import nexus_zkvm_b200 as nb
+        ctx1 = nb.Context(dev.index)          # no communicator: the ordinary single-GPU proof of the same trace
+        p1, _c1, _a1 = M.prove(m, CudaBackend(ctx1), cols, mult, config=CONFIG)
+        same_single = bool(p1 == proof)
+        ctx1.close()
+    h = torch.frombuffer(bytearray(__import__("hashlib").sha256(proof).digest()), dtype=torch.uint8).to(dev)
+    allh = [torch.zeros_like(h) for _ in range(world)]
+    dist.all_gather(allh, h)
+    same = all(bool((x == h).all().item()) for x in allh)
+    ms = float(t.item())
+    return {"ms": ms, "value": (1 << args.log_rows) / (ms * 1e-3), "unit": UNIT, "log_rows": args.log_rows, "scaling": "strong",
+            "same_proof_on_all_ranks": bool(same), "equals_single_gpu_proof": same_single, "proof_bytes": len(proof)}
 
 
 def strong_commit(args, ctx, torch, dist, dev, stream, rank, world, m, reps=3):

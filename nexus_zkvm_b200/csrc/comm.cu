@@ -62,7 +62,12 @@ static NcclApi& nccl() {
   return a;
 }
 
-struct Comm { ncclComm_t comm = nullptr; int rank = 0, world = 1, log_world = 0; };
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, log_world = 0;
+  cudaStream_t side = nullptr;                 // exchanges that overlap the transforms run here (comm_fork / comm_join order it against ctx->stream)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
 
 #define NB_NCCL(ctx, call)                                                                                                        \
   do {                                                                                                                            \
@@ -74,6 +79,9 @@ void comm_release(nb200_ctx* ctx) {
   Comm* c = (Comm*)ctx->comm;
   if (!c) return;
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   ctx->comm = nullptr;
 }
@@ -95,6 +103,67 @@ int comm_rank(const nb200_ctx* ctx) { return ctx->comm ? ((Comm*)ctx->comm)->ran
 int comm_world(const nb200_ctx* ctx) { return ctx->comm ? ((Comm*)ctx->comm)->world : 1; }
 int comm_log_world(const nb200_ctx* ctx) { return ctx->comm ? ((Comm*)ctx->comm)->log_world : 0; }
 void comm_shard_range(size_t total, int world, int rank, size_t* first, size_t* count) { shard_range(total, world, rank, first, count); }
+
+// ---- side stream: the row re-shard of column chunk j travels over NVLink while chunk j + 1 is being transformed on ctx->stream ----
+cudaStream_t comm_side_stream(nb200_ctx* ctx) {
+  Comm* c = (Comm*)ctx->comm;
+  if (!c) return ctx->stream;
+  if (!c->side) {
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); c->side = nullptr; return ctx->stream; }
+  }
+  return c->side;
+}
+// work enqueued on the side stream after this call sees everything enqueued on ctx->stream before it
+nb200_status comm_fork(nb200_ctx* ctx) {
+  cudaStream_t s = comm_side_stream(ctx);
+  if (s == ctx->stream) return NB200_OK;
+  Comm* c = (Comm*)ctx->comm;
+  NB_CUDA(ctx, cudaEventRecord(c->ev_fork, ctx->stream));
+  NB_CUDA(ctx, cudaStreamWaitEvent(s, c->ev_fork, 0));
+  return NB200_OK;
+}
+// ... and the reverse: ctx->stream continues after everything enqueued on the side stream so far
+nb200_status comm_join(nb200_ctx* ctx) {
+  cudaStream_t s = comm_side_stream(ctx);
+  if (s == ctx->stream) return NB200_OK;
+  Comm* c = (Comm*)ctx->comm;
+  NB_CUDA(ctx, cudaEventRecord(c->ev_join, s));
+  NB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_join, 0));
+  return NB200_OK;
+}
+
+// columns -> rows, column chunk j of nch (every rank splits ITS column range into the same number of chunks, so the grouped send / recv pairs match):
+// `src` = base of this rank's columns, `pack` = scratch of (world - 1) x (chunk columns) x (LEN / world) words, everything enqueued on `st`.
+nb200_status exchange_cols_to_rows_chunk(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t total, size_t LEN, u32* dst_rows, u32* pack, int j, int nch) {
+  Comm* c = (Comm*)ctx->comm;
+  const int world = c ? c->world : 1, rank = c ? c->rank : 0;
+  const size_t S = LEN / world;
+  size_t first = 0, count = 0;
+  shard_range(total, world, rank, &first, &count);
+  const size_t c0 = count * j / nch, c1 = count * (j + 1) / nch, nc = c1 - c0;
+  if (nc) NB_CUDA(ctx, cudaMemcpy2DAsync(dst_rows + (first + c0) * S, S * 4, src + c0 * LEN + (size_t)rank * S, LEN * 4, S * 4, nc, cudaMemcpyDeviceToDevice, st));
+  if (world == 1) return NB200_OK;
+  size_t slot = 0;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank || !nc) continue;
+    NB_CUDA(ctx, cudaMemcpy2DAsync(pack + slot * nc * S, S * 4, src + c0 * LEN + (size_t)q * S, LEN * 4, S * 4, nc, cudaMemcpyDeviceToDevice, st));
+    ++slot;
+  }
+  ncclResult_t r = nccl().GroupStart();
+  slot = 0;
+  for (int q = 0; q < world && r == ncclSuccess; ++q) {
+    if (q == rank) continue;
+    size_t qf = 0, qc = 0;
+    shard_range(total, world, q, &qf, &qc);
+    const size_t q0 = qc * j / nch, q1 = qc * (j + 1) / nch;
+    if (nc) { r = nccl().Send(pack + slot * nc * S, nc * S, ncclUint32, q, c->comm, st); ++slot; }
+    if (r == ncclSuccess && q1 > q0) r = nccl().Recv(dst_rows + (qf + q0) * S, (q1 - q0) * S, ncclUint32, q, c->comm, st);
+  }
+  ncclResult_t r2 = nccl().GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) return set_err(ctx, NB200_ERR_CUDA, std::string("exchange cols->rows (chunk): ") + nccl().GetErrorString(r != ncclSuccess ? r : r2));
+  return NB200_OK;
+}
 
 // columns -> rows: `src` = this rank's `count` columns (its shard_range of `total`) of LEN words each; `dst_rows` = all `total` columns restricted to
 // this rank's LEN / world rows.  One strided D2D pack per peer, grouped ncclSend / ncclRecv; a peer's block lands in place (its columns are adjacent).
@@ -172,10 +241,10 @@ nb200_status comm_all_gather_dev(nb200_ctx* ctx, const u32* mine, size_t words, 
   NB_NCCL(ctx, nccl().AllGather(mine, out, words, ncclUint32, c->comm, ctx->stream));
   return NB200_OK;
 }
-nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root) {
+nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root, cudaStream_t st) {
   Comm* c = (Comm*)ctx->comm;
   if (!c) return NB200_OK;
-  NB_NCCL(ctx, nccl().Broadcast(buf, buf, words, ncclUint32, root, c->comm, ctx->stream));
+  NB_NCCL(ctx, nccl().Broadcast(buf, buf, words, ncclUint32, root, c->comm, st ? st : ctx->stream));
   return NB200_OK;
 }
 // element-wise sum of u32 words over the ranks (used where exactly one rank contributes a non-zero word: gathers of owned values)

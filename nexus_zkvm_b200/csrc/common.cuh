@@ -132,7 +132,11 @@ void comm_shard_range(size_t total, int world, int rank, size_t* first, size_t* 
 nb200_status exchange_cols_to_rows(nb200_ctx* ctx, const u32* src, size_t total, size_t LEN, u32* dst_rows);
 nb200_status exchange_rows_to_cols(nb200_ctx* ctx, const u32* src_rows, size_t total, size_t LEN, u32* dst);
 nb200_status comm_all_gather_dev(nb200_ctx* ctx, const u32* mine, size_t words, u32* out);
-nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root);
+nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root, cudaStream_t st = nullptr);
+cudaStream_t comm_side_stream(nb200_ctx* ctx);
+nb200_status comm_fork(nb200_ctx* ctx);
+nb200_status comm_join(nb200_ctx* ctx);
+nb200_status exchange_cols_to_rows_chunk(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t total, size_t LEN, u32* dst_rows, u32* pack, int j, int nch);
 nb200_status comm_all_reduce_sum_host(nb200_ctx* ctx, u32* host, size_t words);
 nb200_status reorder_coset_to_bitrev(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_cols, u32 log_size);
 nb200_status expand_reorder(nb200_ctx* ctx, const void* src, u32 elem_bytes, u32* dst, size_t n_cols, u32 log_size, int coset_order);

@@ -224,37 +224,54 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
   nb200_cols *lde_full = nullptr, *hx_full = nullptr;
   auto fail = [&](nb200_status st) { if (lde_full) nb200_cols_free(ctx, lde_full); if (hx_full) nb200_cols_free(ctx, hx_full); free_tree(ctx, t); return st; };
 #define NB_TRYS(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail(_s); } while (0)
-  // 1. column-sharded transforms of this rank's columns
+  // 1-3. column-sharded transforms of this rank's columns, pipelined with the exchange: the columns are transformed in `nch` chunks on ctx->stream;
+  // as soon as a chunk is done its row slices (LDE, D2, trace rows) travel to their owners on the communicator's side stream while the next
+  // chunk is being transformed.  Every rank uses the same chunk count, so the grouped send / recv pairs of chunk j match.
   NB_TRYS(nb200_cols_alloc(ctx, count, n, &t.big_coeffs));
   NB_TRYS(nb200_cols_alloc(ctx, count, m, &lde_full));
   if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, count, m, &hx_full));
-  if (count) NB_TRYS(commit_transforms(ctx, big_shard->d, t.big_coeffs->d, lde_full->d, hx_full ? hx_full->d : nullptr, count, n, bl));
-  trace_mark(ctx, "sharded commit: ifft+lde (own columns)");
-  // 2. exchange: columns -> row slices (LDE, D2, and the trace rows the interaction trace will read)
   NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows));
-  NB_TRYS(exchange_cols_to_rows(ctx, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d));
-  if (want_hx) {
-    NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows_hx));
-    NB_TRYS(exchange_cols_to_rows(ctx, hx_full->d, total_big, (size_t)1 << m, t.big_rows_hx->d));
+  if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows_hx));
+  if (keep_eval_rows) NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
+  static const int xchg_chunks = [] { const char* e = getenv("NB200_XCHG_CHUNKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
+  const int nch = (world > 1 && total_big / world >= 64) ? xchg_chunks : 1;
+  u32* pack = nullptr;
+  {
+    size_t maxc = 0;
+    for (int r = 0; r < world; ++r) { size_t f, c; comm_shard_range(total_big, world, r, &f, &c); maxc = std::max(maxc, c); }
+    const size_t chunk_cols = (maxc + nch - 1) / nch + 1;
+    if (world > 1) NB_CUDA(ctx, dmalloc(ctx, (void**)&pack, (size_t)(world - 1) * chunk_cols * ((size_t)4 << (m - k))));
   }
-  if (keep_eval_rows) {
-    NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
-    NB_TRYS(exchange_cols_to_rows(ctx, count ? big_shard->d : nullptr, total_big, (size_t)1 << n, t.big_eval_rows->d));
+  cudaStream_t xs = comm_side_stream(ctx);
+  auto fail2 = [&](nb200_status st) { comm_join(ctx); cudaStreamSynchronize(ctx->stream); dfree(ctx, pack); return fail(st); };
+#define NB_TRYX(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail2(_s); } while (0)
+  for (int j = 0; j < nch; ++j) {
+    const size_t c0 = count * j / nch, c1 = count * (j + 1) / nch;
+    if (c1 > c0)
+      NB_TRYX(commit_transforms(ctx, big_shard->d + (c0 << n), t.big_coeffs->d + (c0 << n), lde_full->d + (c0 << m), hx_full ? hx_full->d + (c0 << m) : nullptr, c1 - c0, n, bl));
+    NB_TRYX(comm_fork(ctx));
+    NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d, pack, j, nch));
+    if (want_hx) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, t.big_rows_hx->d, pack, j, nch));
+    if (keep_eval_rows) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, count ? big_shard->d : nullptr, total_big, (size_t)1 << n, t.big_eval_rows->d, pack, j, nch));
   }
-  // 3. columns that constraints read at a row offset: full copies everywhere
+  trace_mark(ctx, "sharded commit: ifft+lde (own columns; exchange overlapped)");
+  NB_TRYX(comm_join(ctx));
+  // columns that constraints read at a row offset: full copies everywhere
   for (size_t i = 0; i < n_replicate; ++i) {
     const size_t g = replicate[i];
-    if (g >= total_big) return fail(set_err(ctx, NB200_ERR_ARG, "commit_sharded: replicate index out of range"));
+    if (g >= total_big) return fail2(set_err(ctx, NB200_ERR_ARG, "commit_sharded: replicate index out of range"));
     if (t.full_lde.count(g)) continue;
     nb200_cols* f = nullptr;
-    NB_TRYS(replicate_column(ctx, lde_full, first, count, g, total_big, m, &f));
+    NB_TRYX(replicate_column(ctx, lde_full, first, count, g, total_big, m, &f));
     t.full_lde[g] = f;
-    if (want_hx) { nb200_cols* h = nullptr; NB_TRYS(replicate_column(ctx, hx_full, first, count, g, total_big, m, &h)); t.full_hx[g] = h; }
+    if (want_hx) { nb200_cols* h = nullptr; NB_TRYX(replicate_column(ctx, hx_full, first, count, g, total_big, m, &h)); t.full_hx[g] = h; }
   }
+#undef NB_TRYX
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, pack);
   nb200_cols_free(ctx, lde_full); lde_full = nullptr;
   if (hx_full) { nb200_cols_free(ctx, hx_full); hx_full = nullptr; }
-  trace_mark(ctx, "sharded commit: exchange");
+  trace_mark(ctx, "sharded commit: exchange tail + replicated columns");
   // 4. the smaller batches: computed in full by every rank
   for (size_t b = 0; b < n_small; ++b) {
     nb200_cols *co = nullptr, *lde = nullptr, *hx = nullptr;

@@ -183,13 +183,31 @@ def prove(machine, backend, main_cols, mult, config=None, associated_data=b"", r
     return proof, claimed, aux
 
 
-def prove_sharded(machine, backend, main_cols, mult, rank, world, config=None, associated_data=b""):
+def shard_host_tree(machine, prover, host_cols, rank, world):
+    """Upload this rank's part of one tree's host columns: (column shard of the leading 2^log_size-row batch or None, its total column count,
+    replicated device batches of the smaller columns)."""
+    from . import Context
+    n, cols = machine.log_size, []
+    for c_ in host_cols:
+        a_ = np.asarray(c_)
+        cols += list(a_) if a_.ndim == 2 else [a_]
+    total_big = 0
+    while total_big < len(cols) and len(cols[total_big]) == 1 << n:
+        total_big += 1
+    assert all(len(c_) < 1 << n for c_ in cols[total_big:]), "the sharded columns must be the leading, largest batch of the tree"
+    first, count = Context.shard_range(total_big, world, rank)
+    shard = prover.ctx.upload(np.stack([np.ascontiguousarray(c_, dtype=np.uint32) for c_ in cols[first:first + count]]), coset_order=True) if count else None
+    small = prover._batches_from_host(cols[total_big:], True) if len(cols) > total_big else []
+    return shard, total_big, small
+
+
+def prove_sharded(machine, backend, main_cols, mult, rank, world, config=None, associated_data=b"", resident=None):
     """ONE proof by `world` GPUs (one process per GPU; `backend.ctx` holds an initialised communicator: Context.comm_init*).  Every rank calls this
     with the same arguments and gets the same proof bytes — the bytes `prove` returns on one GPU.  The Machine::prove order (machine.rs:197-290):
     the main component's columns (the first, largest batch of every tree) are column-sharded over the ranks for the transforms and row-sharded for
     hashing, constraint rows and DEEP quotients; the other components' small columns are replicated.  For the harness every rank is handed the full host
-    trace and uploads only its nb200_shard_range of it (a real host would fill only that range)."""
-    from . import Context
+    trace and uploads only its nb200_shard_range of it (a real host would fill only that range); `resident` = the two shard_host_tree results of
+    trees 0 and 1 when they are already on the device."""
     config = config or dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)
     air, ctx = machine.air, backend.ctx
     ch = backend.channel()
@@ -202,28 +220,14 @@ def prove_sharded(machine, backend, main_cols, mult, rank, world, config=None, a
     n = machine.log_size
     main = air.components[0]
 
-    def flat(cols):
-        out = []
-        for c_ in cols:
-            a_ = np.asarray(c_)
-            out += list(a_) if a_.ndim == 2 else [a_]
-        return [np.ascontiguousarray(x, dtype=np.uint32) for x in out]
-
     def commit_tree(t, host_cols, keep):
-        cols = flat(host_cols)
-        total_big = 0
-        while total_big < len(cols) and len(cols[total_big]) == 1 << n:
-            total_big += 1
-        assert all(len(c_) < 1 << n for c_ in cols[total_big:]), "the sharded columns must be the leading, largest batch of the tree"
-        first, count = Context.shard_range(total_big, world, rank)
-        shard = ctx.upload(np.stack(cols[first:first + count]), coset_order=True) if count else None
-        small = prover._batches_from_host(cols[total_big:], True) if len(cols) > total_big else []
+        shard, total_big, small = resident[t] if resident is not None else shard_host_tree(machine, prover, host_cols, rank, world)
         replicate = sorted({c for (tt, c, off) in main.masks if tt == t and off != 0 and c < total_big})
         root = prover.commit_sharded(shard, total_big, n, small, replicate, keep, ch)
         return root, total_big, shard, small
 
-    root0, big0, shard0, small0 = commit_tree(0, machine.preprocessed_columns(), True)
-    main_part = [main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols)
+    root0, big0, shard0, small0 = commit_tree(0, machine.preprocessed_columns() if resident is None else None, True)
+    main_part = [] if resident is not None else ([main_cols] if getattr(main_cols, "ndim", 1) == 2 else list(main_cols))
     root1, big1, shard1, small1 = commit_tree(1, main_part + ([mult] if mult is not None else []), True)
     params = [(0, 0, 0, 0)] * air.n_params
     for rel in (getattr(machine, "relations", None) or [machine.range256]):

@@ -81,6 +81,22 @@ impl Context {
         }
         Ok(out)
     }
+    /// NCCL communicator of this context (one process per GPU): rank 0 calls `comm_unique_id()`, ships the bytes to the other ranks, all call `comm_init`.
+    pub fn comm_unique_id() -> Result<Vec<u8>> {
+        let mut id = vec![0u8; unsafe { nb200_comm_unique_id_bytes() }];
+        let st = unsafe { nb200_comm_get_unique_id(id.as_mut_ptr()) };
+        if st != NB200_OK { return Err(Error::Backend { status: st, message: "nb200_comm_get_unique_id failed (is libnccl loadable?)".into() }); }
+        Ok(id)
+    }
+    pub fn comm_init(&self, rank: i32, world: i32, unique_id: &[u8]) -> Result<()> {
+        self.check(unsafe { nb200_comm_init(self.raw(), rank, world, unique_id.as_ptr()) })
+    }
+    /// the 16-column-aligned column range rank `rank` of `world` transforms (`nb200_shard_range`)
+    pub fn shard_range(total_cols: usize, world: i32, rank: i32) -> (usize, usize) {
+        let (mut f, mut c) = (0usize, 0usize);
+        unsafe { nb200_shard_range(total_cols, world, rank, &mut f, &mut c) };
+        (f, c)
+    }
     pub fn channel(&self) -> Result<Channel> {
         let mut h = ptr::null_mut();
         self.check(unsafe { nb200_channel_new(self.raw(), &mut h) })?;
@@ -161,6 +177,25 @@ impl Scheme {
         let mut root = [0u8; 32];
         self.ctx.check(unsafe { nb200_scheme_commit(self.h, b.as_ptr(), b.len(), ch.h, root.as_mut_ptr()) })?;
         Ok(root)
+    }
+    /// One proof over N GPUs: the tree's leading `total_big` columns of 2^log_size rows (the main component's) are sharded — `big_shard` is this rank's
+    /// `shard_range` of them — and the smaller batches are replicated; `replicate_cols` lists the big columns the AIR reads at a row offset.
+    /// Call on every rank with the same arguments; returns the root of the WHOLE tree.
+    pub fn commit_sharded(&mut self, big_shard: Option<&Columns>, total_big: usize, log_size: u32, small: &[&Columns], replicate_cols: &[u32],
+                          keep_eval_rows: bool, ch: &mut Channel) -> Result<[u8; 32]> {
+        let b: Vec<*const nb200_cols> = small.iter().map(|c| c.h as *const _).collect();
+        let mut root = [0u8; 32];
+        self.ctx.check(unsafe { nb200_scheme_commit_sharded(self.h, big_shard.map_or(ptr::null(), |c| c.h as *const _), total_big, log_size, b.as_ptr(), b.len(),
+                                                            replicate_cols.as_ptr(), replicate_cols.len(), keep_eval_rows as i32, ch.h, root.as_mut_ptr()) })?;
+        Ok(root)
+    }
+    /// LogUp interaction trace of the sharded (main) component from the trace rows kept by `commit_sharded(.., keep_eval_rows = true, ..)`:
+    /// returns this rank's COLUMN shard of the 4 x n_logup_cols interaction columns and the component's claimed sum (same on every rank).
+    pub fn gen_interaction_trace_sharded(&self, air: &Air, component: u32, params: &[SecureField]) -> Result<(Columns, SecureField)> {
+        let p = secure_to_words(params);
+        let (mut out, mut cs) = (ptr::null_mut(), [0u32; 4]);
+        self.ctx.check(unsafe { nb200_gen_interaction_trace_sharded(self.h, air.h, component, p.as_ptr(), params.len(), &mut out, cs.as_mut_ptr()) })?;
+        Ok((Columns { ctx: self.ctx.clone(), h: out }, words_to_secure(&cs)))
     }
     /// `stwo::prover::prove::<B, Blake2sMerkleChannel>(components, channel, commitment_scheme)` — machine.rs:286-290.
     /// Returns `postcard(StarkProof<Blake2sMerkleHasher>)`.

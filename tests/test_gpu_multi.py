@@ -14,6 +14,57 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _entry(name, rank, world, port, *rest):
+    """Process entry: run the named worker body; an exception is reported through the queue instead of leaving the parent (and the peer, inside a
+    collective) waiting."""
+    q = rest[-1]
+    try:
+        globals()[name](rank, world, port, *rest)
+    except BaseException:   # noqa: BLE001 - reported to the parent, which fails the test
+        import traceback
+        q.put((rank, "worker-error", traceback.format_exc()))
+        q.close(); q.join_thread()
+        os._exit(1)
+
+
+def _run_workers(target, args, world=2, timeout=240):
+    """Spawn `world` workers, collect one result each; the first error (or a silent death / time-out) terminates the others and fails the test."""
+    import queue as _queue
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_entry, args=(target, r, world, port) + tuple(args) + (q,)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, err, deadline = [], None, time.time() + timeout
+    while len(res) < world and err is None:
+        try:
+            item = q.get(timeout=2)
+        except _queue.Empty:
+            if time.time() > deadline:
+                err = "timed out"
+            elif any(p.exitcode not in (None, 0) for p in procs):
+                try:
+                    item = q.get(timeout=2)
+                    err = item[2] if len(item) > 1 and item[1] == "worker-error" else "a worker died"
+                except _queue.Empty:
+                    err = "a worker died without a report"
+            continue
+        if len(item) > 1 and item[1] == "worker-error":
+            err = item[2]
+        else:
+            res.append(item)
+    for p in procs:
+        if err is not None and p.is_alive():
+            p.terminate()
+        p.join(timeout=60)
+    assert err is None, err
+    assert all(p.exitcode == 0 for p in procs)
+    return res
+
+
 def _worker(rank, world, port, n_cols, log_size, q):
     import torch
     import torch.distributed as dist
@@ -111,23 +162,12 @@ def _proof_worker(rank, world, port, kind, log_size, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,log_size", [("add", 10), ("nexus_v1", 12), ("nexus_v1", 16)])
+@pytest.mark.parametrize("kind,log_size", [("add", 12), ("nexus_v1", 12), ("nexus_v1", 16)])
 def test_one_proof_over_two_gpus_matches_single_gpu_bytes(kind, log_size):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_proof_worker, args=(r, world, port, kind, log_size, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = _run_workers("_proof_worker", (kind, log_size), timeout=420)
     single = [s for _, _, s in res if s is not None][0]
     for rank, proof, _ in res:
         assert proof == single, f"rank {rank}: proof bytes differ (len {len(proof)} vs {len(single)})"
@@ -138,22 +178,11 @@ def test_library_sharded_commit_matches_single_gpu_root(n_cols, log_size, small)
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_lib_worker, args=(r, world, port, n_cols, log_size, small, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = _run_workers("_lib_worker", (n_cols, log_size, small))
     single = [s for _, _, s, _, _ in res if s is not None][0]
     for rank, root, _, ok, caps in res:
         assert root == single, f"rank {rank}"
-        assert ok and len(caps) == world
+        assert ok and len(caps) == 2
 
 
 @pytest.mark.parametrize("n_cols,log_size", [(50, 12), (1386, 14)])
@@ -161,18 +190,7 @@ def test_sharded_commit_matches_single_gpu_root(n_cols, log_size):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_cols, log_size, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = _run_workers("_worker", (n_cols, log_size))
     single = [s for _, _, s in res if s is not None][0]
     for rank, root, _ in res:
         assert root == single, f"rank {rank}"
