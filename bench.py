@@ -378,18 +378,8 @@ def main():
     if rank == 0 and not args.no_verify:
         try:
             # the oracle's independent verifier accepts the proof (transcript replayed from the returned roots with the ORACLE's channel)
-            from oracle import pyoracle as orc
-            aux, ch = last["aux"], orc.Channel()
-            for byte in aux["associated_data"]:
-                ch.mix_u64(int(byte))
-            for ls in aux["log_sizes"]:
-                ch.mix_u64(ls)
-            ch.mix_root(aux["roots"][0]); ch.mix_root(aux["roots"][1])
-            for _ in (getattr(m, "relations", None) or [None]):
-                ch.draw_felts(2)                      # LookupElements::draw per relation
-            ch.mix_felts(last["claimed"])
-            ch.mix_root(aux["roots"][2])
-            orc.verify(m.words, np.array(aux["params"], dtype=np.uint32), last["proof"], ch, m.column_log_sizes())
+            from tests.oracle_backend import verify_with_replayed_transcript
+            verify_with_replayed_transcript(m, last["proof"], last["claimed"], last["aux"])
             verified = True
         except Exception as e:
             verified = f"failed: {e!r}"

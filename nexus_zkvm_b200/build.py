@@ -80,7 +80,7 @@ SHIPPED_MACHINES = [(20, 21, False), (22, 21, False), (16, 21, False), (8, 1, Fa
 # prover2-shaped machines (machine.MultiMachine) of tests/test_gpu_prove_parity.py and bench.py --multi: component log sizes
 SHIPPED_MULTI = [list(range(4, 12)), list(range(4, 18)), list(range(4, 22))]
 # the reference's v1 main component as data (nexus_v1.NexusV1Machine): log sizes of the tests, bench.py (16 = CPU sample, 20, 22) and smoke()
-SHIPPED_NEXUS_V1 = [8, 9, 12, 16, 20, 22]
+SHIPPED_NEXUS_V1 = [8, 9, 12, 16, 18, 20, 22, 24]   # 18 / 24: the sharded large-proof test (default size / configs[3])
 
 
 def kernel_sources(words):

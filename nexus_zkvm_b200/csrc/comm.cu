@@ -26,6 +26,8 @@ extern "C" void nb200_cols_free(nb200_ctx*, nb200_cols*);
 extern "C" void nb200_tree_free(nb200_ctx*, nb200_tree*);
 extern "C" nb200_status nb200_hash_node(int merkle_hash, const uint8_t* left, const uint8_t* right, const uint32_t* values, size_t n_values, uint8_t out[32]);
 
+extern "C" nb200_status nb200_comm_all_gather(nb200_ctx* ctx, const uint8_t* mine, size_t bytes, uint8_t* out);
+
 namespace nb {
 
 struct NcclApi {
@@ -67,6 +69,13 @@ struct Comm {
   int rank = 0, world = 1, log_world = 0;
   cudaStream_t side = nullptr;                 // exchanges that overlap the transforms run here (comm_fork / comm_join order it against ctx->stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // symmetric peer heap: cudaMalloc'd segments whose CUDA-IPC handles every rank has opened; all ranks allocate the same sizes in the same order, so
+  // a buffer has the same (segment, offset) everywhere and rank q's copy is reachable as seg.peer[q] + offset (NVLink peer stores / copy engines)
+  struct Seg { u32* base = nullptr; size_t words = 0, used = 0; std::vector<u32*> peer; };
+  std::vector<Seg> heap;
+  int peer_state = -1;                         // -1 not tried, 0 unavailable (exchanges go through NCCL), 1 in use
+  const void* heap_owner = nullptr;            // the scheme whose sharded trees live in the heap (one sharded proof at a time per context)
+  u32* d_flag = nullptr;                       // 1-word buffer of the stream-ordered barrier
 };
 
 #define NB_NCCL(ctx, call)                                                                                                        \
@@ -79,6 +88,11 @@ void comm_release(nb200_ctx* ctx) {
   Comm* c = (Comm*)ctx->comm;
   if (!c) return;
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  for (auto& sg : c->heap) {
+    for (int q = 0; q < (int)sg.peer.size(); ++q) if (q != c->rank && sg.peer[q]) cudaIpcCloseMemHandle(sg.peer[q]);
+    if (sg.base) cudaFree(sg.base);
+  }
+  if (c->d_flag) cudaFree(c->d_flag);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -130,6 +144,122 @@ nb200_status comm_join(nb200_ctx* ctx) {
   Comm* c = (Comm*)ctx->comm;
   NB_CUDA(ctx, cudaEventRecord(c->ev_join, s));
   NB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_join, 0));
+  return NB200_OK;
+}
+
+// stream-ordered barrier: when it completes on this rank's ctx->stream, every rank's stream has reached its own call (all earlier work there is done)
+nb200_status comm_barrier_stream(nb200_ctx* ctx) {
+  Comm* c = (Comm*)ctx->comm;
+  if (!c || c->world == 1) return NB200_OK;
+  if (!c->d_flag) { NB_CUDA(ctx, cudaMalloc((void**)&c->d_flag, 256)); NB_CUDA(ctx, cudaMemsetAsync(c->d_flag, 0, 256, ctx->stream)); }
+  NB_NCCL(ctx, nccl().AllReduce(c->d_flag, c->d_flag, 1, ncclUint32, ncclSum, c->comm, ctx->stream));
+  return NB200_OK;
+}
+
+// ---- symmetric peer heap -------------------------------------------------------------------------------------------------------------------
+static bool all_ranks_agree(nb200_ctx* ctx, Comm* c, int mine) {
+  std::vector<uint8_t> all((size_t)c->world * 4);
+  int32_t v = mine;
+  if (nb200_comm_all_gather(ctx, (const uint8_t*)&v, 4, all.data()) != NB200_OK) return false;
+  for (int q = 0; q < c->world; ++q) { int32_t x; memcpy(&x, &all[(size_t)q * 4], 4); if (!x) return false; }
+  return true;
+}
+// collective: every rank creates a segment of `words`, the IPC handles are all-gathered and opened; on any failure anywhere ALL ranks give the heap up
+static bool peer_new_segment(nb200_ctx* ctx, Comm* c, size_t words) {
+  Comm::Seg sg;
+  sg.words = words;
+  sg.peer.assign(c->world, nullptr);
+  struct Msg { cudaIpcMemHandle_t h; int32_t ok; int32_t pad[3]; } mine;
+  memset(&mine, 0, sizeof mine);
+  bool ok = cudaMalloc((void**)&sg.base, words * 4) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, sg.base) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  mine.ok = ok ? 1 : 0;
+  std::vector<uint8_t> all((size_t)c->world * sizeof(Msg));
+  bool gathered = nb200_comm_all_gather(ctx, (const uint8_t*)&mine, sizeof mine, all.data()) == NB200_OK;
+  bool everyone = gathered;
+  for (int q = 0; q < c->world && everyone; ++q) { Msg m; memcpy(&m, &all[(size_t)q * sizeof(Msg)], sizeof m); if (!m.ok) everyone = false; }
+  bool opened = everyone;
+  if (everyone) {
+    sg.peer[c->rank] = sg.base;
+    for (int q = 0; q < c->world && opened; ++q) {
+      if (q == c->rank) continue;
+      Msg m; memcpy(&m, &all[(size_t)q * sizeof(Msg)], sizeof m);
+      if (cudaIpcOpenMemHandle((void**)&sg.peer[q], m.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); sg.peer[q] = nullptr; opened = false; }
+    }
+  }
+  const bool agreed = gathered && all_ranks_agree(ctx, c, opened ? 1 : 0);
+  if (!agreed) {
+    for (int q = 0; q < c->world; ++q) if (q != c->rank && sg.peer[q]) cudaIpcCloseMemHandle(sg.peer[q]);
+    if (sg.base) cudaFree(sg.base);
+    return false;
+  }
+  c->heap.push_back(std::move(sg));
+  return true;
+}
+// Bump allocation of `words` (the same on every rank, collective when a new segment is needed).  out->d == nullptr: no peer heap (single rank,
+// NB200_PEER_HEAP=0, or CUDA IPC unavailable between the ranks) — the caller uses the NCCL exchange instead; the answer is the same on every rank.
+nb200_status peer_alloc(nb200_ctx* ctx, const void* owner, size_t words, PeerBuf* out) {
+  *out = PeerBuf();
+  Comm* c = (Comm*)ctx->comm;
+  static const bool enabled = [] { const char* e = getenv("NB200_PEER_HEAP"); return !(e && e[0] == '0'); }();
+  if (!c || c->world == 1 || !enabled || c->peer_state == 0) return NB200_OK;
+  if (c->heap_owner && c->heap_owner != owner) {
+    bool any = false;
+    for (auto& sg : c->heap) any = any || sg.used;
+    NB_ARG(ctx, !any, "peer heap: one sharded proof at a time per context (free the previous scheme first)");
+  }
+  c->heap_owner = owner;
+  words = (words + 63) & ~(size_t)63;                    // 256-byte granules
+  for (size_t i = 0; i < c->heap.size(); ++i) {
+    auto& sg = c->heap[i];
+    if (sg.words - sg.used >= words) { out->d = sg.base + sg.used; out->seg = (int)i; out->off = sg.used; sg.used += words; return NB200_OK; }
+  }
+  static const size_t min_seg = [] { const char* e = getenv("NB200_PEER_SEG_MIB"); size_t v = e ? (size_t)atoll(e) : 4096; return (v < 64 ? 64 : v) << 18; }();   // words
+  if (!peer_new_segment(ctx, c, std::max(words, min_seg))) { c->peer_state = 0; return NB200_OK; }
+  c->peer_state = 1;
+  auto& sg = c->heap.back();
+  out->d = sg.base; out->seg = (int)c->heap.size() - 1; out->off = 0; sg.used = words;
+  return NB200_OK;
+}
+u32* peer_ptr(nb200_ctx* ctx, const PeerBuf& b, int q) {
+  Comm* c = (Comm*)ctx->comm;
+  return c->heap[b.seg].peer[q] + b.off;
+}
+// every allocation of `owner` is released (the memory stays mapped for the next proof)
+void peer_heap_release(nb200_ctx* ctx, const void* owner) {
+  Comm* c = ctx ? (Comm*)ctx->comm : nullptr;
+  if (!c || c->heap_owner != owner) return;
+  for (auto& sg : c->heap) sg.used = 0;
+  c->heap_owner = nullptr;
+}
+
+// columns -> rows straight into the owners' row-slice buffers (peer heap): one strided 2-D copy per destination rank — no pack buffer, no NCCL
+// staging, no SMs (copy engines over NVLink), so it overlaps the transforms of the next column chunk for real.  Chunking as in the NCCL variant.
+nb200_status peer_cols_to_rows_chunk(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t total, size_t LEN, const PeerBuf& dst_rows, int j, int nch) {
+  Comm* c = (Comm*)ctx->comm;
+  const int world = c->world, rank = c->rank;
+  const size_t S = LEN / world;
+  size_t first = 0, count = 0;
+  shard_range(total, world, rank, &first, &count);
+  const size_t c0 = count * j / nch, c1 = count * (j + 1) / nch, nc = c1 - c0;
+  if (!nc) return NB200_OK;
+  for (int d = 0; d < world; ++d) {
+    const int q = (rank + d) % world;                    // own slice first, then the peers in a rotated order (spreads the NVLink targets)
+    NB_CUDA(ctx, cudaMemcpy2DAsync(peer_ptr(ctx, dst_rows, q) + (first + c0) * S, S * 4, src + c0 * LEN + (size_t)q * S, LEN * 4, S * 4, nc, cudaMemcpyDefault, st));
+  }
+  return NB200_OK;
+}
+// rows -> columns: this rank's S rows of rank q's columns go into q's column shard (peer heap) at row offset rank * S
+nb200_status peer_rows_to_cols(nb200_ctx* ctx, cudaStream_t st, const u32* src_rows, size_t total, size_t LEN, const PeerBuf& dst_shard) {
+  Comm* c = (Comm*)ctx->comm;
+  const int world = c->world, rank = c->rank;
+  const size_t S = LEN / world;
+  for (int d = 0; d < world; ++d) {
+    const int q = (rank + d) % world;
+    size_t qf = 0, qc = 0;
+    shard_range(total, world, q, &qf, &qc);
+    if (qc) NB_CUDA(ctx, cudaMemcpy2DAsync(peer_ptr(ctx, dst_shard, q) + (size_t)rank * S, LEN * 4, src_rows + qf * S, S * 4, S * 4, qc, cudaMemcpyDefault, st));
+  }
   return NB200_OK;
 }
 

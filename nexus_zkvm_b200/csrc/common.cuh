@@ -133,6 +133,14 @@ nb200_status exchange_cols_to_rows(nb200_ctx* ctx, const u32* src, size_t total,
 nb200_status exchange_rows_to_cols(nb200_ctx* ctx, const u32* src_rows, size_t total, size_t LEN, u32* dst);
 nb200_status comm_all_gather_dev(nb200_ctx* ctx, const u32* mine, size_t words, u32* out);
 nb200_status comm_broadcast_dev(nb200_ctx* ctx, u32* buf, size_t words, int root, cudaStream_t st = nullptr);
+// symmetric peer heap (CUDA IPC over NVLink): see comm.cu
+struct PeerBuf { u32* d = nullptr; int seg = -1; size_t off = 0; };
+nb200_status peer_alloc(nb200_ctx* ctx, const void* owner, size_t words, PeerBuf* out);
+u32* peer_ptr(nb200_ctx* ctx, const PeerBuf& b, int q);
+void peer_heap_release(nb200_ctx* ctx, const void* owner);
+nb200_status peer_cols_to_rows_chunk(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t total, size_t LEN, const PeerBuf& dst_rows, int j, int nch);
+nb200_status peer_rows_to_cols(nb200_ctx* ctx, cudaStream_t st, const u32* src_rows, size_t total, size_t LEN, const PeerBuf& dst_shard);
+nb200_status comm_barrier_stream(nb200_ctx* ctx);
 cudaStream_t comm_side_stream(nb200_ctx* ctx);
 nb200_status comm_fork(nb200_ctx* ctx);
 nb200_status comm_join(nb200_ctx* ctx);

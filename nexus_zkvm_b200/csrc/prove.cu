@@ -230,9 +230,21 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
   NB_TRYS(nb200_cols_alloc(ctx, count, n, &t.big_coeffs));
   NB_TRYS(nb200_cols_alloc(ctx, count, m, &lde_full));
   if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, count, m, &hx_full));
-  NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows));
-  if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows_hx));
-  if (keep_eval_rows) NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
+  // the row-slice buffers: in the symmetric peer heap when CUDA IPC links the ranks (the owners of the columns then write their rows straight into
+  // them over NVLink with the copy engines), else ordinary allocations filled by grouped ncclSend / ncclRecv
+  PeerBuf pb_rows, pb_hx, pb_ev;
+  NB_TRYS(peer_alloc(ctx, s, total_big << (m - k), &pb_rows));
+  const bool peer = pb_rows.d != nullptr;
+  if (peer) {
+    NB_TRYS(nb200_cols_from_device(ctx, pb_rows.d, total_big, m - k, &t.big_rows));
+    if (want_hx) { NB_TRYS(peer_alloc(ctx, s, total_big << (m - k), &pb_hx)); NB_ARG(ctx, pb_hx.d, "peer heap"); NB_TRYS(nb200_cols_from_device(ctx, pb_hx.d, total_big, m - k, &t.big_rows_hx)); }
+    if (keep_eval_rows) { NB_TRYS(peer_alloc(ctx, s, total_big << (n - k), &pb_ev)); NB_ARG(ctx, pb_ev.d, "peer heap"); NB_TRYS(nb200_cols_from_device(ctx, pb_ev.d, total_big, n - k, &t.big_eval_rows)); }
+    NB_TRYS(comm_barrier_stream(ctx));     // every rank has reached this commit: nobody still reads what these buffers held in the previous proof
+  } else {
+    NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows));
+    if (want_hx) NB_TRYS(nb200_cols_alloc(ctx, total_big, m - k, &t.big_rows_hx));
+    if (keep_eval_rows) NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
+  }
   static const int xchg_chunks = [] { const char* e = getenv("NB200_XCHG_CHUNKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
   const int nch = (world > 1 && total_big / world >= 64) ? xchg_chunks : 1;
   u32* pack = nullptr;
@@ -240,7 +252,7 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
     size_t maxc = 0;
     for (int r = 0; r < world; ++r) { size_t f, c; comm_shard_range(total_big, world, r, &f, &c); maxc = std::max(maxc, c); }
     const size_t chunk_cols = (maxc + nch - 1) / nch + 1;
-    if (world > 1) NB_CUDA(ctx, dmalloc(ctx, (void**)&pack, (size_t)(world - 1) * chunk_cols * ((size_t)4 << (m - k))));
+    if (world > 1 && !peer) NB_CUDA(ctx, dmalloc(ctx, (void**)&pack, (size_t)(world - 1) * chunk_cols * ((size_t)4 << (m - k))));
   }
   cudaStream_t xs = comm_side_stream(ctx);
   auto fail2 = [&](nb200_status st) { comm_join(ctx); cudaStreamSynchronize(ctx->stream); dfree(ctx, pack); return fail(st); };
@@ -250,12 +262,19 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
     if (c1 > c0)
       NB_TRYX(commit_transforms(ctx, big_shard->d + (c0 << n), t.big_coeffs->d + (c0 << n), lde_full->d + (c0 << m), hx_full ? hx_full->d + (c0 << m) : nullptr, c1 - c0, n, bl));
     NB_TRYX(comm_fork(ctx));
-    NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d, pack, j, nch));
-    if (want_hx) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, t.big_rows_hx->d, pack, j, nch));
-    if (keep_eval_rows) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, count ? big_shard->d : nullptr, total_big, (size_t)1 << n, t.big_eval_rows->d, pack, j, nch));
+    if (peer) {
+      NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, pb_rows, j, nch));
+      if (want_hx) NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, pb_hx, j, nch));
+      if (keep_eval_rows && count) NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, big_shard->d, total_big, (size_t)1 << n, pb_ev, j, nch));
+    } else {
+      NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d, pack, j, nch));
+      if (want_hx) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, t.big_rows_hx->d, pack, j, nch));
+      if (keep_eval_rows) NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, count ? big_shard->d : nullptr, total_big, (size_t)1 << n, t.big_eval_rows->d, pack, j, nch));
+    }
   }
   trace_mark(ctx, "sharded commit: ifft+lde (own columns; exchange overlapped)");
   NB_TRYX(comm_join(ctx));
+  if (peer) NB_TRYX(comm_barrier_stream(ctx));   // my copies are done AND (the barrier completing) so are everybody's into my buffers
   // columns that constraints read at a row offset: full copies everywhere
   for (size_t i = 0; i < n_replicate; ++i) {
     const size_t g = replicate[i];
@@ -1141,8 +1160,20 @@ nb200_status gen_interaction_sharded(nb200_scheme* s, nb200_air* air_h, u32 comp
   // rows -> this rank's column shard
   size_t first = 0, count = 0;
   comm_shard_range(total, world, rank, &first, &count);
-  if (st == NB200_OK) st = nb200_cols_alloc(ctx, count, n, &shard.c);
-  if (st == NB200_OK) st = exchange_rows_to_cols(ctx, rows.c->d, total, N, shard.c->d);
+  PeerBuf pb_shard;
+  size_t maxc = 0;
+  for (int r = 0; r < world; ++r) { size_t f, cn; comm_shard_range(total, world, r, &f, &cn); maxc = std::max(maxc, cn); }
+  if (st == NB200_OK) st = peer_alloc(ctx, s, maxc << n, &pb_shard);      // the same size on every rank (symmetric offsets)
+  if (st == NB200_OK && pb_shard.d) {
+    // peer heap: my rows of rank q's columns go straight into q's shard (copy engines over NVLink); valid until the scheme is freed
+    st = nb200_cols_from_device(ctx, pb_shard.d, count, n, &shard.c);
+    if (st == NB200_OK) st = comm_barrier_stream(ctx);
+    if (st == NB200_OK) st = peer_rows_to_cols(ctx, ctx->stream, rows.c->d, total, N, pb_shard);
+    if (st == NB200_OK) st = comm_barrier_stream(ctx);
+  } else {
+    if (st == NB200_OK) st = nb200_cols_alloc(ctx, count, n, &shard.c);
+    if (st == NB200_OK) st = exchange_rows_to_cols(ctx, rows.c->d, total, N, shard.c->d);
+  }
   cudaStreamSynchronize(ctx->stream);
   trace_mark(ctx, "logup: rows -> columns exchange");
   dfree(ctx, d_params);
@@ -1238,6 +1269,7 @@ uint32_t nb200_air_max_log_expand(const nb200_air* a) {
 void nb200_scheme_free(nb200_scheme* s) {
   if (!s) return;
   for (auto& t : s->trees) free_tree(s->ctx, t);
+  peer_heap_release(s->ctx, s);
   delete s;
 }
 nb200_status nb200_scheme_commit(nb200_scheme* s, const nb200_cols* const* eval_batches, size_t n_batches, nb200_channel* channel, uint8_t root[32]) {

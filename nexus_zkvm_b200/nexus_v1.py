@@ -384,5 +384,84 @@ class NexusV1Machine:
         assert len(cols) == self.air.n_columns()[1]
         return cols
 
+    # ---- rank-local witness generation (one proof over N GPUs at sizes whose full trace no single host process should build) ----
+    def fill_main_trace_shard(self, seed, first, count):
+        """Main columns [first, first + count) of a padding-only witness, generated WITHOUT building the other columns: every word draws from its
+        own generator keyed by (seed, word name), so any column range gives the same values whichever rank asks.  Same constraints as
+        `fill_main_trace`, a different random stream.  Returns (columns, partial Range256 histogram, partial Range32 histogram): the two
+        multiplicity columns are the sums of the partial histograms over a partition of the 347 columns (`multiplicity_columns`)."""
+        import zlib
+        n = 1 << self.log_size
+        sizes = dict(MAIN_COLUMNS)
+        index = [(name, k) for name, size in MAIN_COLUMNS for k in range(size)]
+        assert 0 <= first and first + count <= len(index)
+        ones = {"IsPadding", "ValueAEffectiveFlagAux", "ValueAEffectiveFlagAuxInv"}
+        ts_words = {f"{pre}Reg{k}TsPrev": k for k in (1, 2, 3) for pre in ("", "C")}
+        ts_words.update({f"CH{k}Minus": k for k in (1, 2, 3)})
+        nibbles = {"ValueA4_7": "ValueA", "ValueB4_7": "ValueB", "ValueC4_7": "ValueC"}
+        free = set(R256_WORDS + R256_HALF_WORDS + R256_BYTES + ["Reg1ValPrev", "Reg2ValPrev", "Reg3ValPrev", "PcNext"]) - {"ValueAEffective"} - set(ts_words)
+        rng_of = lambda tag: np.random.default_rng([int(seed) & 0xFFFFFFFF, zlib.crc32(tag.encode())])
+        cache = {}
+
+        def timestamps(k):
+            if ("ts", k) not in cache:
+                clk = np.arange(1, n + 1, dtype=np.uint64)
+                cur = 3 * clk + k
+                prev = (rng_of(f"ts{k}").integers(0, 1 << 62, n, dtype=np.uint64) % cur).astype(np.uint64)
+                cc = cur - 1 - prev
+                b0 = (((cc & 0xFFFF) + (prev & 0xFFFF) + 1) >> 16).astype(np.uint32)
+                cache[("ts", k)] = (prev, cc, b0)
+            return cache[("ts", k)]
+
+        def word(name):
+            """all limbs of one word"""
+            if name in cache:
+                return cache[name]
+            size = sizes[name]
+            if name in ones:
+                limbs = [np.ones(n, np.uint32) for _ in range(size)]
+            elif name in ts_words:
+                prev, cc, b0 = timestamps(ts_words[name])
+                src = b0 if name.startswith("CH") else (cc if name.startswith("C") else prev)
+                if name.startswith("CH"):    # the borrow of the low 16 bits; the second limb (high borrow) is 0 for these values
+                    limbs = [b0] + [np.zeros(n, np.uint32) for _ in range(size - 1)]
+                else:
+                    limbs = [((src >> (8 * i)) & 0xFF).astype(np.uint32) for i in range(4)]
+            elif name in nibbles:
+                limbs = [v >> 4 for v in word(nibbles[name])]
+            elif name in ("OpB", "Reg1Address", "Reg2Address", "Reg3Address"):
+                limbs = [rng_of(name).integers(0, 32, n, dtype=np.uint64).astype(np.uint32)]
+            elif name in free:
+                g = rng_of(name)
+                limbs = [g.integers(0, 256, n, dtype=np.uint64).astype(np.uint32) for _ in range(size)]
+                if name == "Pc":
+                    for limb in limbs:
+                        limb[0] = 0
+            else:
+                limbs = [np.zeros(n, np.uint32) for _ in range(size)]
+            cache[name] = limbs
+            return limbs
+
+        cols, h256, h32 = [], np.zeros(256, np.int64), np.zeros(32, np.int64)
+        r256 = set(R256_WORDS + R256_HALF_WORDS + R256_BYTES)
+        for name, k in index[first:first + count]:
+            col = word(name)[k]
+            cols.append(col)
+            if name in r256:
+                h256 += np.bincount(col, minlength=256)
+            if name in R32:
+                h32 += np.bincount(col, minlength=32)
+        return cols, h256, h32
+
+    @staticmethod
+    def multiplicity_columns(h256, h32):
+        """The two extension multiplicity columns (tree 1's small columns) from the histograms summed over all main columns."""
+        return [(np.asarray(h256, np.int64) % P).astype(np.uint32), (np.asarray(h32, np.int64) % P).astype(np.uint32)]
+
+    def preprocessed_shard(self, first, count):
+        """Columns [first, first + count) of the 27 big preprocessed columns (a (count, 2^log_size) uint32 array) and the two table columns."""
+        cols = self._preprocessed_list()
+        return np.stack(cols[:27][first:first + count]).astype(np.uint32) if count else None, cols[27:]
+
     def column_log_sizes(self):
         return self.air.column_log_sizes()

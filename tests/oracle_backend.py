@@ -42,3 +42,20 @@ class OracleBackend:
 
 def verify(machine, proof, aux):
     orc.verify(machine.words, np.array(aux["params"], dtype=np.uint32), proof, aux["channel_at_prove"], machine.column_log_sizes())
+
+
+def verify_with_replayed_transcript(machine, proof, claimed, aux):
+    """The oracle's verifier on a proof produced elsewhere (the GPU): the transcript is replayed with the ORACLE's channel from the values the
+    prover returned (associated data, log sizes, the three roots, claimed sums) in Machine::prove's order (machine.rs:197-263)."""
+    ch = orc.Channel()
+    for byte in aux["associated_data"]:
+        ch.mix_u64(int(byte))
+    for ls in aux["log_sizes"]:
+        ch.mix_u64(ls)
+    ch.mix_root(aux["roots"][0])
+    ch.mix_root(aux["roots"][1])
+    for _ in (getattr(machine, "relations", None) or [None]):
+        ch.draw_felts(2)                      # LookupElements::draw per relation
+    ch.mix_felts(claimed)
+    ch.mix_root(aux["roots"][2])
+    orc.verify(machine.words, np.array(aux["params"], dtype=np.uint32), proof, ch, machine.column_log_sizes())

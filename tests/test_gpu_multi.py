@@ -162,6 +162,87 @@ def _proof_worker(rank, world, port, kind, log_size, q):
         dist.destroy_process_group()
 
 
+def _large_worker(rank, world, port, log_rows, q):
+    """configs[3]'s shape: ONE proof of the v1 main component at 2^log_rows rows over ALL ranks, every rank generating only ITS column shard of the
+    witness (NexusV1Machine.fill_main_trace_shard); rank 0 checks the proof with the oracle's verifier."""
+    import time
+    import torch
+    import torch.distributed as dist
+    import nexus_zkvm_b200 as nb
+    from nexus_zkvm_b200 import machine as M
+    from nexus_zkvm_b200.nexus_v1 import NexusV1Machine
+    from nexus_zkvm_b200.prover import CudaBackend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        config = dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)
+        ctx = nb.Context(rank)
+        ctx.comm_init_from_torch(dist, dev)
+        t0 = time.perf_counter()
+        m = NexusV1Machine(log_rows)
+        be = CudaBackend(ctx)
+        pr = be.prover(m.words, config)
+        f0, c0 = nb.Context.shard_range(27, world, rank)
+        pre, tables = m.preprocessed_shard(f0, c0)
+        res0 = (ctx.upload(pre, coset_order=True) if c0 else None, 27, pr._batches_from_host(tables, True))
+        del pre
+        f1, c1 = nb.Context.shard_range(m.n_main, world, rank)
+        cols, h256, h32 = m.fill_main_trace_shard(5, f1, c1)
+        hist = torch.from_numpy(np.concatenate([h256, h32])).to(dev)
+        dist.all_reduce(hist)
+        hist = hist.cpu().numpy()
+        shard1 = ctx.upload(np.stack(cols), coset_order=True) if c1 else None
+        del cols
+        res1 = (shard1, m.n_main, pr._batches_from_host(m.multiplicity_columns(hist[:256], hist[256:]), True))
+        del pr
+        t_fill = time.perf_counter() - t0
+        times = []
+        for rep in range(2):
+            dist.barrier(); torch.cuda.synchronize()
+            t = time.perf_counter()
+            proof, claimed, aux = M.prove_sharded(m, be, None, None, rank, world, config=config, associated_data=b"lg", resident=[res0, res1])
+            ctx.sync()
+            times.append(time.perf_counter() - t)
+        ok = None
+        if rank == 0:
+            from tests.oracle_backend import verify_with_replayed_transcript
+            verify_with_replayed_transcript(m, proof, claimed, aux)      # raises on a rejected proof
+            ok = M.verify_claimed_sums(claimed)
+        import hashlib
+        q.put((rank, hashlib.sha256(proof).hexdigest(), ok, len(proof), times, t_fill))
+        ctx.sync()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_large_proof_over_all_gpus_is_accepted_by_the_verifier():
+    """BASELINE configs[3]'s shape.  NB200_LARGE_LOG_ROWS (default 18) rows over the largest power-of-two number of GPUs on the box (set
+    NB200_LARGE_WORLD to use fewer); `NB200_LARGE_LOG_ROWS=24` on 8 GPUs is configs[3] itself.  The timing goes to gpurun_out/ when that exists."""
+    import json
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 1 << (n_dev.bit_length() - 1)
+    world = min(world, int(os.environ.get("NB200_LARGE_WORLD", world)))
+    log_rows = int(os.environ.get("NB200_LARGE_LOG_ROWS", "18"))
+    res = _run_workers("_large_worker", (log_rows,), world=world, timeout=900)
+    hashes = {h for _, h, _, _, _, _ in res}
+    assert len(hashes) == 1, "the ranks hold different proofs"
+    r0 = [r for r in res if r[0] == 0][0]
+    assert r0[2] is True
+    out = {"log_rows": log_rows, "world": world, "proof_bytes": r0[3], "accepted_by_oracle_verifier": True,
+           "prove_s_per_rank": {str(r[0]): r[4] for r in res}, "fill_and_upload_s": {str(r[0]): r[5] for r in res}}
+    print(json.dumps(out))
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, f"large_proof_2p{log_rows}_n{world}.json"), "w") as f:
+            json.dump(out, f)
+
+
 @pytest.mark.parametrize("kind,log_size", [("add", 12), ("nexus_v1", 12), ("nexus_v1", 16)])
 def test_one_proof_over_two_gpus_matches_single_gpu_bytes(kind, log_size):
     import torch
