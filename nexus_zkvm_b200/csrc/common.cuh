@@ -121,7 +121,11 @@ nb200_status fft_interpolate(nb200_ctx* ctx, const u32* src, u32* dst, size_t n_
 // Circle FFT: coefficients (src, log src_log) zero-extended to dst (log dst_log); src may equal dst if logs match
 nb200_status fft_evaluate(nb200_ctx* ctx, const u32* src, u32 src_log, u32* dst, u32 dst_log, size_t n_cols, u32 tw_log = 0);
 // evaluations -> coefficients + LDE (+ optionally the half-coset extension the quotient step needs) for one batch (fft_fused.cu)
-nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 log_size, u32 log_blowup);
+// destination of a row-sharded commitment: rank q's row-slice buffers (2^log_slice rows of every column) as mapped in THIS process
+struct RowScatter { int world = 1; u32 log_slice = 0; size_t col0 = 0; u32* lde_rows[16] = {nullptr}; u32* hx_rows[16] = {nullptr}; };
+nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 log_size, u32 log_blowup,
+                               const RowScatter* scatter = nullptr, bool* scattered = nullptr);
+bool commit_transforms_can_scatter(u32 n, u32 bl, u32 log_slice, int world);
 void fft_fused_release(nb200_ctx* ctx);
 // ---- multi-GPU plumbing (comm.cu): NCCL over the ranks that prove one trace together; all no-ops / local copies without a communicator
 void comm_release(nb200_ctx* ctx);

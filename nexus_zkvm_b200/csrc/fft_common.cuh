@@ -5,6 +5,9 @@
 
 namespace nb {
 
+#ifndef NB_MAX_SHARD_RANKS
+#define NB_MAX_SHARD_RANKS 16
+#endif
 struct FftPass {
   const u32* src;     // source columns (column c at src + c*src_stride); zero-extended beyond src_len
   u32* dst;           // destination columns
@@ -23,6 +26,11 @@ struct FftPass {
   u32 apply_scale;
   u32 tn;             // log size of the canonic domain whose twiddle arrays are used (= n, or n + 1 for the half-domain transforms)
   u32 ztop;           // forward transforms of zero-extended input: layers >= ztop are copies (= log2 of the source length)
+  // row-sharded destination (one proof over N GPUs): rows [q << shard_log, (q + 1) << shard_log) of every column belong to rank q, whose row-slice
+  // buffer (column stride 2^shard_log) is mapped at shard_dst[q] — peer memory over NVLink for q != this rank.  0 = off (dst / dst_stride are used).
+  u32 shard_log = 0;
+  size_t shard_col0 = 0;  // index of this batch's column 0 inside the row-slice buffers
+  u32* shard_dst[NB_MAX_SHARD_RANKS] = {nullptr};
 };
 
 __device__ __forceinline__ void butterfly(u32& v0, u32& v1, u32 t) {

@@ -77,12 +77,12 @@ __device__ __forceinline__ void stage_in_async(const TileGeo<T, W>& geo, const u
 }
 
 template <int T, int W, int CB>
-__device__ __forceinline__ void stage_out(const TileGeo<T, W>& geo, const u32* sm, u32* __restrict__ dst, size_t dst_stride, u32 col0, u32 ncb) {
+__device__ __forceinline__ void stage_out(const TileGeo<T, W>& geo, const u32* sm, u32* __restrict__ dst, size_t dst_stride, u32 col0, u32 ncb, size_t gsub = 0) {
   constexpr int NT = 1 << (T - 4);
 #pragma unroll
   for (int c = 0; c < CB; ++c) {
     if (c < (int)ncb) {
-      u32* __restrict__ dcol = dst + (size_t)(col0 + c) * dst_stride;
+      u32* __restrict__ dcol = dst + (size_t)(col0 + c) * dst_stride - gsub;
 #pragma unroll
       for (int it = 0; it < 4; ++it)
         *reinterpret_cast<uint4*>(dcol + geo.g0 + it * geo.gstep) = *reinterpret_cast<const uint4*>(sm + (c << T) + geo.phys0 + it * NT * 4);
@@ -223,7 +223,14 @@ __global__ void __launch_bounds__(1 << (T - 4), MINB) fft_tile_async_kernel(cons
     tile_round<INV, T, W, CB, RI, false, RR == 0, 0, PROD>(p.tw2, p.ctw2, p.tw_len, p.tn, lo, tile_hi, sm, sm, ncb, 0u, ptw2, cptw2);
     __syncthreads();
   });
-  stage_out<T, W, CB>(geo, sm, p.dst, p.dst_stride, col0, ncb);
+  if (W == 0 && p.shard_log) {
+    // the tile's rows all belong to one rank: the finished tile goes straight into that rank's row-slice buffer (a peer store over NVLink unless it
+    // is ours) — the re-shard of the commitment happens here, tile by tile, while the other CTAs are still computing
+    const u32 q = (u32)(gbase >> p.shard_log);
+    stage_out<T, W, CB>(geo, sm, p.shard_dst[q] + (p.shard_col0 << p.shard_log), (size_t)1 << p.shard_log, col0, ncb, (size_t)q << p.shard_log);
+  } else {
+    stage_out<T, W, CB>(geo, sm, p.dst, p.dst_stride, col0, ncb);
+  }
 }
 
 // ================================================================================================================
@@ -295,8 +302,16 @@ static nb200_status set_smem(nb200_ctx* ctx, K kernel, size_t smem, bool* flags)
 }
 
 template <bool INV, int T, int CB, int MINB, bool PROD = false>
-static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t src_stride, u32* dst, size_t dst_stride, size_t n_cols, u32 n, u32 tn) {
+static nb200_status launch_contig(nb200_ctx* ctx, cudaStream_t st, const u32* src, size_t src_stride, u32* dst, size_t dst_stride, size_t n_cols, u32 n, u32 tn,
+                                  const RowScatter* sc = nullptr, int which = 0) {
   FftPass p;
+  p.shard_log = 0; p.shard_col0 = 0;
+  for (int q = 0; q < NB_MAX_SHARD_RANKS; ++q) p.shard_dst[q] = nullptr;
+  if (sc) {
+    NB_ARG(ctx, !INV && sc->world <= NB_MAX_SHARD_RANKS && sc->log_slice >= (u32)T && sc->log_slice <= n, "row scatter: slice smaller than a tile");
+    p.shard_log = sc->log_slice; p.shard_col0 = sc->col0;
+    for (int q = 0; q < sc->world; ++q) p.shard_dst[q] = which ? sc->hx_rows[q] : sc->lde_rows[q];
+  }
   p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride; p.src_len = (size_t)1 << n;
   p.tw = INV ? ctx->tw.d_itw : ctx->tw.d_tw;
   p.tw2 = INV ? ctx->tw.d_itw2 : ctx->tw.d_tw2;
@@ -353,7 +368,7 @@ static nb200_status chunk_streams(nb200_ctx* ctx) {
 
 // evals (n_cols x 2^n, read only) -> coeffs (n_cols x 2^n) and lde (n_cols x 2^(n+bl)); optionally half_ext (n_cols x 2^(n+bl)):
 // the same polynomials on the first half of CanonicCoset(n+bl+1).circle_domain() (fft.cu's half-domain transform).
-nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 n, u32 bl) {
+nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 n, u32 bl, const RowScatter* scatter) {
   if (n_cols == 0) return NB200_OK;
   FusedPlan pl;
   NB_ARG(ctx, fused_plan(n, &pl) && bl >= 1 && bl <= 2, "commit transforms: unsupported shape for the fused pipeline");
@@ -418,15 +433,18 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
     }
     // C: the contiguous low layers of every forward transform (each 2^n-word block is independent below layer n: run them as
     // one launch over the 2^m-word columns)
-    auto fwd_low = [&](u32* buf, u32 tn) -> nb200_status {
-      if (pl.LA != 12) return launch_contig<false, 13, 2, 2>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
-      if (var_c == 1) return launch_contig<false, 12, 3, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
-      if (var_c == 2) return launch_contig<false, 12, 2, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
-      if (var_c == 3) return launch_contig<false, 12, 4, 3, true>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
-      return launch_contig<false, 12, 4, 3>(ctx, st, buf, mlen, buf, mlen, nc, m, tn);
+    RowScatter sc_chunk;
+    if (scatter) { sc_chunk = *scatter; sc_chunk.col0 += c0; }
+    const RowScatter* scp = scatter ? &sc_chunk : nullptr;
+    auto fwd_low = [&](u32* buf, u32 tn, int which) -> nb200_status {
+      if (pl.LA != 12) return launch_contig<false, 13, 2, 2>(ctx, st, buf, mlen, buf, mlen, nc, m, tn, scp, which);
+      if (var_c == 1) return launch_contig<false, 12, 3, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn, scp, which);
+      if (var_c == 2) return launch_contig<false, 12, 2, 4>(ctx, st, buf, mlen, buf, mlen, nc, m, tn, scp, which);
+      if (var_c == 3) return launch_contig<false, 12, 4, 3, true>(ctx, st, buf, mlen, buf, mlen, nc, m, tn, scp, which);
+      return launch_contig<false, 12, 4, 3>(ctx, st, buf, mlen, buf, mlen, nc, m, tn, scp, which);
     };
-    NB_TRY(fwd_low(lde + c0 * mlen, m));
-    if (half_ext) NB_TRY(fwd_low(half_ext + c0 * mlen, m + 1));
+    NB_TRY(fwd_low(lde + c0 * mlen, m, 0));
+    if (half_ext) NB_TRY(fwd_low(half_ext + c0 * mlen, m + 1, 1));
   }
   if (multi) {
     for (int i = 0; i < 2; ++i) {
@@ -438,14 +456,29 @@ nb200_status fft_commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs
 }
 
 // TreeBuilder::extend_evals + the LDE of TreeBuilder::commit for one batch: the fused pipeline when the shape allows, else per-transform passes
-nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 n, u32 bl) {
+// `scatter` (one proof over N GPUs): the last pass of the LDE (and of the D2 evaluation) stores every finished tile into the row-slice buffer of the
+// rank that owns its rows instead of `lde` / `half_ext` (which then hold intermediates only); *scattered tells the caller whether that happened — the
+// per-transform fallback cannot, and leaves complete columns in `lde` / `half_ext` for a copy-based re-shard.
+nb200_status commit_transforms(nb200_ctx* ctx, const u32* evals, u32* coeffs, u32* lde, u32* half_ext, size_t n_cols, u32 n, u32 bl, const RowScatter* scatter, bool* scattered) {
+  if (scattered) *scattered = false;
   if (n_cols == 0) return NB200_OK;
-  if (fft_fused_supported(n, bl, evals, coeffs, lde) && (!half_ext || (bl == 1 && ((uintptr_t)half_ext & 15u) == 0)))
-    return fft_commit_transforms(ctx, evals, coeffs, lde, half_ext, n_cols, n, bl);
+  if (fft_fused_supported(n, bl, evals, coeffs, lde) && (!half_ext || (bl == 1 && ((uintptr_t)half_ext & 15u) == 0))) {
+    FusedPlan pl;
+    const bool can = scatter && scattered && fused_plan(n, &pl) && scatter->world <= NB_MAX_SHARD_RANKS && scatter->log_slice >= pl.LA;
+    if (scattered) *scattered = can;
+    return fft_commit_transforms(ctx, evals, coeffs, lde, half_ext, n_cols, n, bl, can ? scatter : nullptr);
+  }
   NB_TRY(fft_interpolate(ctx, evals, coeffs, n_cols, n));
   NB_TRY(fft_evaluate(ctx, coeffs, n, lde, n + bl, n_cols));
   if (half_ext) NB_TRY(fft_evaluate(ctx, coeffs, n, half_ext, n + bl, n_cols, n + bl + 1));
   return NB200_OK;
+}
+
+// can the last LDE pass store straight into row-slice buffers of 2^log_slice rows?  (the same answer on every rank: it depends on sizes only)
+bool commit_transforms_can_scatter(u32 n, u32 bl, u32 log_slice, int world) {
+  FusedPlan pl;
+  static const int fused = env_int("NB200_FFT_FUSED", 1);
+  return fused && bl == 1 && fused_plan(n, &pl) && world <= NB_MAX_SHARD_RANKS && log_slice >= pl.LA;
 }
 
 void fft_fused_release(nb200_ctx* ctx) {

@@ -195,14 +195,10 @@ nb200_status scheme_commit_host(nb200_scheme* s, const void* const* host, const 
 // exchange per committed tree and evaluation set (comm.cu); the few columns read at a row offset (`Pc`, `IsPadding`, the last LogUp column) are
 // replicated; everything small (extension components, composition tree, FRI) is computed redundantly on every rank.
 // ======================================================================================================================================
-static nb200_status replicate_column(nb200_ctx* ctx, const nb200_cols* own_cols /* own_count x LEN */, size_t own_first, size_t own_count, size_t g, size_t total,
-                                     u32 log_len, nb200_cols** out) {
+// a column the constraints read at a row offset: every rank needs all of it — the all-gather of its row slices (contiguous row ranges in rank order)
+static nb200_status replicate_from_rows(nb200_ctx* ctx, const nb200_cols* rows, size_t g, u32 log_len, nb200_cols** out) {
   NB_TRY(nb200_cols_alloc(ctx, 1, log_len, out));
-  int owner = 0;
-  for (int r = 0; r < comm_world(ctx); ++r) { size_t f, c; comm_shard_range(total, comm_world(ctx), r, &f, &c); if (g >= f && g < f + c) owner = r; }
-  if (g >= own_first && g < own_first + own_count)
-    NB_CUDA(ctx, cudaMemcpyAsync((*out)->d, own_cols->col(g - own_first), ((size_t)4) << log_len, cudaMemcpyDeviceToDevice, ctx->stream));
-  return comm_broadcast_dev(ctx, (*out)->d, (size_t)1 << log_len, owner);
+  return comm_all_gather_dev(ctx, rows->col(g), (size_t)1 << rows->log_size, (*out)->d);
 }
 
 nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard, size_t total_big, u32 n, const nb200_cols* const* small, size_t n_small,
@@ -246,7 +242,16 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
     if (keep_eval_rows) NB_TRYS(nb200_cols_alloc(ctx, total_big, n - k, &t.big_eval_rows));
   }
   static const int xchg_chunks = [] { const char* e = getenv("NB200_XCHG_CHUNKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 64 ? 64 : v); }();
-  const int nch = (world > 1 && total_big / world >= 64) ? xchg_chunks : 1;
+  // with the peer heap and a fused-pipeline size the LAST PASS of the transforms stores every finished tile into its owner's row-slice buffer (NVLink
+  // peer stores from the kernel: compute and exchange are one launch); otherwise the columns are transformed in chunks and re-sharded by copies /
+  // NCCL on the side stream while the next chunk is transformed
+  const bool scatter_ok = peer && commit_transforms_can_scatter(n, bl, m - k, world);
+  RowScatter sc;
+  if (scatter_ok) {
+    sc.world = world; sc.log_slice = m - k; sc.col0 = first;
+    for (int q = 0; q < world; ++q) { sc.lde_rows[q] = peer_ptr(ctx, pb_rows, q); sc.hx_rows[q] = want_hx ? peer_ptr(ctx, pb_hx, q) : nullptr; }
+  }
+  const int nch = (!scatter_ok && world > 1 && total_big / world >= 64) ? xchg_chunks : 1;
   u32* pack = nullptr;
   {
     size_t maxc = 0;
@@ -259,12 +264,20 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
 #define NB_TRYX(expr) do { nb200_status _s = (expr); if (_s != NB200_OK) return fail2(_s); } while (0)
   for (int j = 0; j < nch; ++j) {
     const size_t c0 = count * j / nch, c1 = count * (j + 1) / nch;
-    if (c1 > c0)
-      NB_TRYX(commit_transforms(ctx, big_shard->d + (c0 << n), t.big_coeffs->d + (c0 << n), lde_full->d + (c0 << m), hx_full ? hx_full->d + (c0 << m) : nullptr, c1 - c0, n, bl));
+    bool scattered = false;
+    if (c1 > c0) {
+      RowScatter scj = sc;
+      scj.col0 = first + c0;
+      NB_TRYX(commit_transforms(ctx, big_shard->d + (c0 << n), t.big_coeffs->d + (c0 << n), lde_full->d + (c0 << m), hx_full ? hx_full->d + (c0 << m) : nullptr, c1 - c0, n, bl,
+                                scatter_ok ? &scj : nullptr, &scattered));
+      if (scatter_ok && !scattered) return fail2(set_err(ctx, NB200_ERR_STATE, "commit_sharded: the fused pipeline refused the row scatter"));
+    }
     NB_TRYX(comm_fork(ctx));
     if (peer) {
-      NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, pb_rows, j, nch));
-      if (want_hx) NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, pb_hx, j, nch));
+      if (!scatter_ok) {
+        NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, pb_rows, j, nch));
+        if (want_hx) NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, hx_full->d, total_big, (size_t)1 << m, pb_hx, j, nch));
+      }
       if (keep_eval_rows && count) NB_TRYX(peer_cols_to_rows_chunk(ctx, xs, big_shard->d, total_big, (size_t)1 << n, pb_ev, j, nch));
     } else {
       NB_TRYX(exchange_cols_to_rows_chunk(ctx, xs, lde_full->d, total_big, (size_t)1 << m, t.big_rows->d, pack, j, nch));
@@ -281,9 +294,9 @@ nb200_status scheme_commit_sharded(nb200_scheme* s, const nb200_cols* big_shard,
     if (g >= total_big) return fail2(set_err(ctx, NB200_ERR_ARG, "commit_sharded: replicate index out of range"));
     if (t.full_lde.count(g)) continue;
     nb200_cols* f = nullptr;
-    NB_TRYX(replicate_column(ctx, lde_full, first, count, g, total_big, m, &f));
+    NB_TRYX(replicate_from_rows(ctx, t.big_rows, g, m, &f));
     t.full_lde[g] = f;
-    if (want_hx) { nb200_cols* h = nullptr; NB_TRYX(replicate_column(ctx, hx_full, first, count, g, total_big, m, &h)); t.full_hx[g] = h; }
+    if (want_hx) { nb200_cols* h = nullptr; NB_TRYX(replicate_from_rows(ctx, t.big_rows_hx, g, m, &h)); t.full_hx[g] = h; }
   }
 #undef NB_TRYX
   NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
