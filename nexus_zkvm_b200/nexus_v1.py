@@ -385,7 +385,7 @@ class NexusV1Machine:
         return cols
 
     # ---- rank-local witness generation (one proof over N GPUs at sizes whose full trace no single host process should build) ----
-    def fill_main_trace_shard(self, seed, first, count):
+    def fill_main_trace_shard(self, seed, first, count, out=None):
         """Main columns [first, first + count) of a padding-only witness, generated WITHOUT building the other columns: every word draws from its
         own generator keyed by (seed, word name), so any column range gives the same values whichever rank asks.  Same constraints as
         `fill_main_trace`, a different random stream.  Returns (columns, partial Range256 histogram, partial Range32 histogram): the two
@@ -409,7 +409,7 @@ class NexusV1Machine:
                 cur = 3 * clk + k
                 prev = (rng_of(f"ts{k}").integers(0, 1 << 62, n, dtype=np.uint64) % cur).astype(np.uint64)
                 cc = cur - 1 - prev
-                b0 = (((cc & 0xFFFF) + (prev & 0xFFFF) + 1) >> 16).astype(np.uint32)
+                b0 = (((cc & 0xFFFF) + (prev & 0xFFFF) + 1) >> 16).astype(np.uint8)
                 cache[("ts", k)] = (prev, cc, b0)
             return cache[("ts", k)]
 
@@ -419,49 +419,79 @@ class NexusV1Machine:
                 return cache[name]
             size = sizes[name]
             if name in ones:
-                limbs = [np.ones(n, np.uint32) for _ in range(size)]
+                limbs = [np.ones(n, np.uint8) for _ in range(size)]
             elif name in ts_words:
                 prev, cc, b0 = timestamps(ts_words[name])
                 src = b0 if name.startswith("CH") else (cc if name.startswith("C") else prev)
                 if name.startswith("CH"):    # the borrow of the low 16 bits; the second limb (high borrow) is 0 for these values
-                    limbs = [b0] + [np.zeros(n, np.uint32) for _ in range(size - 1)]
+                    limbs = [b0] + [np.zeros(n, np.uint8) for _ in range(size - 1)]
                 else:
-                    limbs = [((src >> (8 * i)) & 0xFF).astype(np.uint32) for i in range(4)]
+                    limbs = [((src >> (8 * i)) & 0xFF).astype(np.uint8) for i in range(4)]
             elif name in nibbles:
                 limbs = [v >> 4 for v in word(nibbles[name])]
             elif name in ("OpB", "Reg1Address", "Reg2Address", "Reg3Address"):
-                limbs = [rng_of(name).integers(0, 32, n, dtype=np.uint64).astype(np.uint32)]
+                limbs = [rng_of(name).integers(0, 32, n, dtype=np.uint8)]
             elif name in free:
                 g = rng_of(name)
-                limbs = [g.integers(0, 256, n, dtype=np.uint64).astype(np.uint32) for _ in range(size)]
+                limbs = [g.integers(0, 256, n, dtype=np.uint8) for _ in range(size)]      # every limb is a byte: kept as bytes until it is stored
                 if name == "Pc":
                     for limb in limbs:
                         limb[0] = 0
             else:
-                limbs = [np.zeros(n, np.uint32) for _ in range(size)]
+                limbs = [np.zeros(n, np.uint8) for _ in range(size)]
             cache[name] = limbs
             return limbs
 
         cols, h256, h32 = [], np.zeros(256, np.int64), np.zeros(32, np.int64)
         r256 = set(R256_WORDS + R256_HALF_WORDS + R256_BYTES)
-        for name, k in index[first:first + count]:
+        for i, (name, k) in enumerate(index[first:first + count]):
             col = word(name)[k]
-            cols.append(col)
+            if out is not None:                  # a preallocated (count, 2^log_size) block, e.g. pinned host memory
+                out[i] = col
+            else:
+                cols.append(col.astype(np.uint32))
             if name in r256:
                 h256 += np.bincount(col, minlength=256)
             if name in R32:
                 h32 += np.bincount(col, minlength=32)
-        return cols, h256, h32
+        return (out if out is not None else cols), h256, h32
 
     @staticmethod
     def multiplicity_columns(h256, h32):
         """The two extension multiplicity columns (tree 1's small columns) from the histograms summed over all main columns."""
         return [(np.asarray(h256, np.int64) % P).astype(np.uint32), (np.asarray(h32, np.int64) % P).astype(np.uint32)]
 
-    def preprocessed_shard(self, first, count):
-        """Columns [first, first + count) of the 27 big preprocessed columns (a (count, 2^log_size) uint32 array) and the two table columns."""
-        cols = self._preprocessed_list()
-        return np.stack(cols[:27][first:first + count]).astype(np.uint32) if count else None, cols[27:]
+    def preprocessed_shard(self, first, count, out=None):
+        """Columns [first, first + count) of the 27 big preprocessed columns (a (count, 2^log_size) uint32 array; `out` = a preallocated one) and
+        the two table columns; only the requested columns are generated."""
+        n = 1 << self.log_size
+        ids = self.air.preprocessed_ids
+        tables = [np.arange(256, dtype=np.uint32), np.arange(32, dtype=np.uint32)]
+        assert ids["Range256Values"] == 27 and ids["Range32Values"] == 28
+        if not count:
+            return None, tables
+        by_id = {}
+        for name in ("IsFirst", "IsLast"):
+            by_id[ids[f"{name}_0"]] = (name, 0)
+        for name in ("Clk", "Reg1TsCur", "Reg2TsCur", "Reg3TsCur"):
+            for k in range(4):
+                by_id[ids[f"{name}_{k}"]] = (name, k)
+        block = out if out is not None else np.empty((count, n), np.uint32)
+        clk = None
+        for i in range(count):
+            name, k = by_id.get(first + i, (None, 0))
+            if name is None:                       # program columns: all zero (empty program)
+                block[i] = 0
+            elif name == "IsFirst":
+                block[i] = 0; block[i, 0] = 1
+            elif name == "IsLast":
+                block[i] = 0; block[i, n - 1] = 1
+            else:
+                if clk is None:
+                    clk = np.arange(1, n + 1, dtype=np.uint64)
+                v = clk if name == "Clk" else 3 * clk + int(name[3])
+                block[i] = (v >> (8 * k)) & 0xFF
+        return block, tables
 
     def column_log_sizes(self):
         return self.air.column_log_sizes()

@@ -31,7 +31,7 @@ def _run_workers(target, args, world=2, timeout=240):
     """Spawn `world` workers, collect one result each; the first error (or a silent death / time-out) terminates the others and fails the test."""
     import queue as _queue
     import time
-    import torch.multiprocessing as mp
+    import multiprocessing as mp      # the parent only needs Process / Queue (torch is imported by the workers)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -186,16 +186,16 @@ def _large_worker(rank, world, port, log_rows, q):
         be = CudaBackend(ctx)
         pr = be.prover(m.words, config)
         f0, c0 = nb.Context.shard_range(27, world, rank)
-        pre, tables = m.preprocessed_shard(f0, c0)
+        pre, tables = m.preprocessed_shard(f0, c0, out=ctx.host_alloc(c0, log_rows) if c0 else None)     # pinned staging blocks
         res0 = (ctx.upload(pre, coset_order=True) if c0 else None, 27, pr._batches_from_host(tables, True))
         del pre
         f1, c1 = nb.Context.shard_range(m.n_main, world, rank)
-        cols, h256, h32 = m.fill_main_trace_shard(5, f1, c1)
+        block, h256, h32 = m.fill_main_trace_shard(5, f1, c1, out=ctx.host_alloc(c1, log_rows) if c1 else None)
         hist = torch.from_numpy(np.concatenate([h256, h32])).to(dev)
         dist.all_reduce(hist)
         hist = hist.cpu().numpy()
-        shard1 = ctx.upload(np.stack(cols), coset_order=True) if c1 else None
-        del cols
+        shard1 = ctx.upload(block, coset_order=True) if c1 else None
+        del block
         res1 = (shard1, m.n_main, pr._batches_from_host(m.multiplicity_columns(hist[:256], hist[256:]), True))
         del pr
         t_fill = time.perf_counter() - t0
@@ -278,3 +278,27 @@ def test_sharded_commit_matches_single_gpu_root(n_cols, log_size):
     single = [s for _, _, s in res if s is not None][0]
     for rank, root, _ in res:
         assert root == single, f"rank {rank}"
+
+
+if __name__ == "__main__":
+    # python tests/test_gpu_multi.py --large 24 --world 8 : the large sharded proof without pytest (the parent process never imports torch)
+    import argparse
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--large", type=int, default=18)
+    ap.add_argument("--world", type=int, default=2)
+    ap.add_argument("--timeout", type=int, default=600)
+    a = ap.parse_args()
+    res = _run_workers("_large_worker", (a.large,), world=a.world, timeout=a.timeout)
+    assert len({h for _, h, _, _, _, _ in res}) == 1, "the ranks hold different proofs"
+    r0 = [r for r in res if r[0] == 0][0]
+    assert r0[2] is True
+    out = {"log_rows": a.large, "world": a.world, "proof_bytes": r0[3], "accepted_by_oracle_verifier": True,
+           "prove_s_per_rank": {str(r[0]): r[4] for r in res}, "fill_and_upload_s": {str(r[0]): r[5] for r in res}}
+    print(json.dumps(out))
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, f"large_proof_2p{a.large}_n{a.world}.json"), "w") as f:
+            json.dump(out, f)

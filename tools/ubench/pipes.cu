@@ -21,6 +21,20 @@ template <int OP> __device__ __forceinline__ void step(u32& a, u32& b, const u32
                  u32 x = a + t; u32 y = a - t; a = min(x, x - P31); b = min(y, y + P31); }
   if (OP == 9) { asm volatile("add.u32 %0, %1, %2;" : "=r"(a) : "r"(a), "r"(c)); }                                            // IADD (which pipe?)
   if (OP == 10) { u64 p; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(a), "r"(c), "l"((u64)b << 32 | a)); a = (u32)(p >> 32); }  // IMAD.WIDE with 64-bit addend
+  // butterfly variants that move the two plain adds to the FMA pipe as integer multiply-adds (x * (+-1) + y); the constants sit in registers
+  if (OP == 12) { u64 p = (u64)b * c; u32 s = ((u32)p >> 1) + (u32)(p >> 32); u32 t = min(s, s - P31); u32 x, y;
+                  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x) : "r"(t), "r"(1u), "r"(a));
+                  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(y) : "r"(t), "r"(0xffffffffu), "r"(a));
+                  a = min(x, x - P31); b = min(y, y + P31); }
+  if (OP == 13) { u64 p = (u64)b * c; u32 s = ((u32)p >> 1) + (u32)(p >> 32); u32 t = min(s, s - P31); u32 y;                    // only the subtraction on the FMA pipe
+                  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(y) : "r"(t), "r"(0xffffffffu), "r"(a));
+                  u32 x = a + t; a = min(x, x - P31); b = min(y, y + P31); }
+  if (OP == 14) { u64 p = (u64)b * c; u32 lo = (u32)p, hi = (u32)(p >> 32), s;                                                     // ... and the fold as shift (ALU) + IMAD add instead of LEA.HI
+                  u32 h = lo >> 1; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(h), "r"(1u), "r"(hi));
+                  u32 t = min(s, s - P31); u32 x, y;
+                  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x) : "r"(t), "r"(1u), "r"(a));
+                  asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(y) : "r"(t), "r"(0xffffffffu), "r"(a));
+                  a = min(x, x - P31); b = min(y, y + P31); }
   if (OP == 11) { u32 h; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(c)); u32 l = a * (c >> 1); asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(h), "r"(0x80000001u), "r"(l)); }  // Shoup-style product: HI + LO + MAD (all FMA pipe)
 }
 template <int OP> __global__ void k(u32* out, u32 c0, long long* cyc) {
@@ -64,6 +78,9 @@ int main() {
     run<7>("m31_mul_dbl (WIDE+LEA.HI+VIADDMNMX)", 3, d_out, d_cyc, w);
     run<11>("Shoup product (HI+LO+MAD)", 3, d_out, d_cyc, w);
     run<8>("butterfly (7 instr)", 7, d_out, d_cyc, w);
+    run<12>("butterfly, add and sub as IMAD (FMA pipe)", 7, d_out, d_cyc, w);
+    run<13>("butterfly, sub as IMAD", 7, d_out, d_cyc, w);
+    run<14>("butterfly, add/sub/fold-add as IMAD", 8, d_out, d_cyc, w);
     printf("\n");
   }
   return 0;
