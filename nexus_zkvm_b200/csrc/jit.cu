@@ -20,6 +20,15 @@
 
 namespace nb {
 
+// threads per CTA the constraint kernels are compiled for (their __launch_bounds__): 1024 -> <= 64 registers per thread; NB200_JIT_BOUND=512 lets
+// the compiler use up to 128 (fewer spills of the chunk state, half the warps per SM) — a tuning knob, part of the generated source and so of its cache key
+static u32 jit_bound() {
+  static u32 v = 0;
+  if (!v) { v = JIT_BLOCK; if (const char* e = getenv("NB200_JIT_BOUND")) { int x = atoi(e); if (x == 256 || x == 512 || x == 1024) v = (u32)x; } }
+  return v;
+}
+
+
 namespace {
 struct Nvrtc {
   void* h = nullptr;
@@ -240,7 +249,7 @@ std::string gen_source(const AirComponent& c) {
   // The CTAs re-converge (__syncthreads) after every chunk: the warps of a CTA then execute the same few tens of KB of straight-line
   // code at a time and the instruction cache serves them from one fetch.  Without the barriers the warps drift apart over the ~0.7 MB
   // program and the kernel is instruction-fetch bound (ncu: stall_no_instruction 11 per issue, icc hit rate 53 %).
-  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
+  o << "extern \"C\" __global__ void __launch_bounds__(" << jit_bound() << ", 1) nbjit(const u32* const* __restrict__ cols, const u32* __restrict__ params, const u32* __restrict__ coeff,\n"
     << "    const u32* __restrict__ dinv, u32* __restrict__ a0, u32* __restrict__ a1, u32* __restrict__ a2, u32* __restrict__ a3, u32 EL, u32 row0) {\n"
     << "  const u32 row = row0 + blockIdx.x * blockDim.x + threadIdx.x;   // row0: a rank of a multi-GPU proof evaluates its slice of the domain's rows\n  St s;\n"
     << "  for (int i = 0; i < " << nb << "; ++i) s.b[i] = 0u;\n  for (int i = 0; i < " << ne << "; ++i) s.e[i] = Q{0u, 0u, 0u, 0u};\n  s.rr = Q{0u, 0u, 0u, 0u};\n";
@@ -343,7 +352,7 @@ std::string jit_logup_source(const AirComponent& c) { return gen_logup_source(c)
 static u32 jit_block() {
   static u32 b = 0;
   if (!b) { b = 512; if (const char* e = getenv("NB200_JIT_BLOCK")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) b = (u32)v; } }
-  return b;
+  return b < jit_bound() ? b : jit_bound();
 }
 
 bool jit_enabled() {
