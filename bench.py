@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 P = (1 << 31) - 1
 METRIC = "RISC-V cycles proved/sec @ 2^20 rows"
 UNIT = "cycles/s"
-STRONG_VALIDATED_WORLDS = {2}          # world sizes on which tests/test_gpu_multi.py ran the sharded commit / sharded proof on real GPUs
+STRONG_VALIDATED_WORLDS = {2, 4, 8}    # world sizes on which the sharded commit / sharded proof ran on real GPUs this round (profiles/bench_n{2,4,8}_r02*.json)
 CONFIG = dict(pow_bits=5, log_blowup=1, log_last=0, n_queries=3)   # PcsConfig::default() as restated in DESIGN.md
 
 
