@@ -230,6 +230,11 @@ impl Recorder {
         for (n2, d2) in &fr[1..] { let nn = d2.clone() * num.clone() + den.clone() * n2.clone(); den = den * d2.clone(); num = nn; }
         (num, den)
     }
+    /// number of secure LogUp columns this component adds to the interaction tree (`finalize_logup*`: one per batch) — 4 base-field
+    /// coordinate columns each
+    pub fn n_logup_columns(&self) -> usize {
+        self.g.borrow().batching.as_ref().map_or(0, |b| b.iter().copied().max().map_or(0, |m| m + 1))
+    }
     /// Serialise this component (call after `FrameworkEval::evaluate(recorder)` returned it).
     pub fn finish(self) -> Vec<u32> {
         assert!(self.pending_fracs.is_empty() || self.g.borrow().batching.is_some(), "logup fractions were added but finalize_logup was not called");
