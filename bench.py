@@ -18,7 +18,11 @@ decommitments and the postcard proof bytes.  Host-side trace FILLING is outside 
           u8, the device widens them and applies finalize_columns) -> proof bytes on the host; H2D and D2H inside the timed region;
   stages / roofline   the commit transforms (iFFT + LDE of every committed column: the dominant kernel group) timed alone with
           CUDA events on the launching stream, against MEASURED_PEAKS.json's HBM bandwidth at 12 algorithmic bytes per trace element;
-  N > 1   weak scaling: every rank proves its own 2^log_rows-row trace segment; the Merkle roots are all-gathered over NCCL.
+  N > 1   `value` is weak scaling: every rank proves its own 2^log_rows-row trace segment; the Merkle roots are all-gathered over NCCL.
+          Two strong-scaling legs follow (on the world sizes the sharded paths were validated on: STRONG_VALIDATED_WORLDS): `strong_commit` = one
+          1012-column tree committed by all ranks through nb200_commit_sharded, and `strong_proof` = ONE whole 2^log_rows-row proof by all ranks
+          together (machine.prove_sharded: column-/row-sharded main component, re-shard fused into the last LDE pass over NVLink), whose bytes are
+          compared with the single-GPU proof inside the run.
 Inputs (1.4 GB of evaluations, 45 GB of intermediates per proof) are far larger than L2: no flush is needed between steps.
 """
 import argparse
